@@ -1,0 +1,73 @@
+"""CPU, only where /root/reference was compiled (oracle/_ref): the restatement against
+the live reference on inputs the fixtures do not cover (odd d, tiny lists, k > list)."""
+import numpy as np
+import pytest
+
+from auncel_b200 import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built here")
+
+
+def test_low_level_kernels():
+    lib = O.ref()
+    x = synth.clustered(1, 64, 40)
+    y = synth.clustered(2, 64, 40)
+    for d in (1, 2, 3, 4, 5, 7, 8, 13, 32, 39, 40):
+        for i in range(64):
+            a, b = np.ascontiguousarray(x[i, :d]), np.ascontiguousarray(y[i, :d])
+            assert O.fvec_L2sqr(a, b) == lib.ref_fvec_L2sqr(O._p(a, O._f), O._p(b, O._f), d)
+            assert O.fvec_inner_product(a, b) == lib.ref_fvec_inner_product(O._p(a, O._f), O._p(b, O._f), d)
+    err = O.C.c_int(0)
+    for a, b, c in [(1.0, 2.0, 3.0), (0.5, 0.5, 1e-3), (3.25, 7.5, 0.125), (1e4, 2e4, 5e3)]:
+        assert O.orc().orc_cosine_theorem(a, b, c, O.C.byref(err)) == lib.ref_cosine_theorem(a, b, c)
+
+
+@pytest.mark.parametrize("metric,d", [(O.L2, 10), (O.L2, 32), (O.IP, 12)])
+def test_fixed_search_small(metric, d):
+    O.RefIndex.set_blas_threshold(1 << 30)
+    nlist, nb, nq, k = 32, 1000, 50, 10
+    xb = synth.clustered(5, nb, d, 20, 0.3, normalize=metric == O.IP)
+    xq = synth.clustered(6, nq, d, 20, 0.3, normalize=metric == O.IP)
+    R = O.RefIndex(d, nlist, metric)
+    R.train(xb, niter=3)
+    R.add(xb)
+    orc = O.OracleIndex(d, nlist, metric)
+    orc.set_centroids(R.centroids())
+    orc.add(xb)
+    for nprobe in (1, 4, 32):
+        D1, I1 = R.search_fixed(xq, k, nprobe)
+        D2, I2 = orc.search_fixed(xq, k, nprobe)
+        assert np.array_equal(D1, D2) and np.array_equal(I1, I2)
+    # k larger than what nprobe=1 can return: -1 / FLT_MAX padding (Heap.h:295-322)
+    D1, I1 = R.search_fixed(xq, 100, 1)
+    D2, I2 = orc.search_fixed(xq, 100, 1)
+    assert np.array_equal(D1, D2) and np.array_equal(I1, I2)
+    assert (I1 == -1).any()
+    R.close()
+
+
+def test_shards_match_merge_tables():
+    O.RefIndex.set_blas_threshold(1 << 30)
+    d, nlist, nb, nq, k = 16, 32, 3000, 40, 10
+    xb = synth.clustered(7, nb, d, 20, 0.3)
+    xq = synth.clustered(8, nq, d, 20, 0.3)
+    full = O.RefIndex(d, nlist, O.L2)
+    full.train(xb, niter=3)
+    full.add(xb)
+    cent = full.centroids()
+    subs = []
+    for s in range(3):
+        r = O.RefIndex(d, nlist, O.L2)
+        r.set_centroids(cent)
+        O._ck(O.ref().ref_copy_subset_to(full.h, r.h, 1, 3, s))  # id % 3 == s
+        subs.append(r)
+    Dm, Im = O.ref_shards_search(subs, xq, k, 4)
+    Df, If = full.search_fixed(xq, k, 4)
+    assert np.array_equal(Dm, Df)  # tests/test_merge.cpp invariant
+    allD = np.stack([r.search_fixed(xq, k, 4)[0] for r in subs])
+    allI = np.stack([r.search_fixed(xq, k, 4)[1] for r in subs])
+    D2, I2 = O.merge_tables(O.L2, allD, allI)
+    assert np.array_equal(D2, Dm) and np.array_equal(I2, Im)
+    for r in subs + [full]:
+        r.close()
