@@ -1,0 +1,185 @@
+// Internal C++ engine behind the C ABI (include/auncel_b200.h).
+// One IvfIndex = one device-resident IndexIVFFlat (centroids + inverted lists) together
+// with Auncel's error model and the scratch arenas the query path needs.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "errmodel.h"
+
+namespace auncel {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define AUNCEL_THROW(code, msg) throw ::auncel::Error(code, std::string(msg) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")")
+#define AUNCEL_CHECK(cond, msg) do { if (!(cond)) AUNCEL_THROW(-2, std::string("Error: '" #cond "' failed: ") + msg); } while (0)
+#define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) AUNCEL_THROW(-4, std::string("CUDA error: ") + cudaGetErrorString(e_) + " in " #x); } while (0)
+
+// grow-only device buffer
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    T* ensure(size_t n) {
+        if (n > cap) {
+            release();
+            size_t want = n + n / 8 + 16;
+            CUDA_CHECK(cudaMalloc(&p, want * sizeof(T)));
+            cap = want;
+        }
+        return p;
+    }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+template <typename T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    T* ensure(size_t n) {
+        if (n > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            CUDA_CHECK(cudaMallocHost(&p, (n + 16) * sizeof(T)));
+            cap = n + 16;
+        }
+        return p;
+    }
+};
+
+constexpr int MAX_K = 128;          // widest result heap the fused selection supports
+constexpr int SCAN_QT = 32;         // queries per scan tile
+constexpr int SCAN_VT = 128;        // list vectors per pipeline block
+constexpr int SCAN_DK = 32;         // floats per k-chunk
+constexpr int SCAN_THREADS = 256;
+
+struct SearchStats {  // IndexIVFStats, IndexIVF.h:361-374
+    uint64_t nq = 0, nlist = 0, ndis = 0, nheap_updates = 0;
+    double quantization_ms = 0, search_ms = 0;
+    uint64_t rounds = 0, scan_tiles = 0, scan_pairs = 0;
+    double scan_ms = 0;      // device time of the scan kernels of the last search
+    uint64_t err_bits = 0;   // ERR_* bits raised by the last search
+};
+
+// per-query arguments of a search call; all pointers are DEVICE pointers
+struct QueryBatch {
+    long n = 0;
+    const float* x = nullptr;  // n x d
+    int k = 0;                 // result width (max_topk in tune mode)
+    int nprobe = 0;
+    long max_codes = 0;
+    int mode = 0;              // 0 fixed, 1 tune (error bounded), 2 training (calibration)
+    int query_topk = 0;
+    const float* require_acc = nullptr;  // n
+    const float* gt_kth = nullptr;       // n, GT distance at rank query_topk-1 (profile)
+    unsigned long long* my_nprobe = nullptr;  // n, in/out
+    float* t_recalls = nullptr;          // n, in/out
+    int profile = 0, overhead_profile = 0;
+    float* D = nullptr;       // n x k
+    long long* I = nullptr;   // n x k
+    float* snapshots = nullptr;  // training: n x n_traces x k sorted distances
+    float* dtb_out = nullptr;    // optional n x max_num (training needs it on the host)
+};
+
+struct IvfIndex {
+    int d = 0, dpad = 0;
+    long nlist = 0;
+    int metric = METRIC_L2;
+    int device = 0;
+    long ntotal = 0;
+    bool trained = false;
+
+    // device-resident index
+    DevBuf<float> centroids;   // nlist x dpad
+    DevBuf<float> interdis;    // nlist*(nlist-1)/2, packed triangle (Auncel's interdis_cem)
+    bool have_interdis = false;
+    DevBuf<float> codes;       // ntotal x dpad, lists concatenated in list order
+    DevBuf<long long> ids;     // ntotal
+    DevBuf<long long> list_off;  // nlist + 1 (in vectors)
+    std::vector<long long> h_list_off;
+
+    // error model (device copies + host mirror)
+    std::vector<float> h_arcos;
+    std::vector<long> h_trace_off;
+    std::vector<float> h_phi, h_U, h_sigma;
+    DevBuf<float> d_arcos, d_phi, d_U, d_sigma;
+    DevBuf<long> d_trace_off;
+    float multipler = 1.f, std_m = 1.f;
+    int n_traces = 0;
+
+    // scratch (grow-only)
+    DevBuf<float> q_x;         // staged queries (n x dpad)
+    DevBuf<float> c_raw;       // unranked coarse distances (one chunk)
+    DevBuf<float> c_dis;       // n x nlist coarse distances, ranked
+    DevBuf<int> c_keys;        // n x nlist ranked centroid ids
+    DevBuf<float> dtb;         // n x max_num
+    DevBuf<unsigned char> state;  // per-query running state, see search.cu
+    DevBuf<unsigned char> pool;
+    DevBuf<int> slot_cnt;
+    DevBuf<int> active, active2;
+    DevBuf<int> list_cnt, list_pair_off, list_tile_off, list_cursor;
+    DevBuf<unsigned long long> pairs;
+    DevBuf<int> ctl;           // small control block (counters)
+    PinnedBuf<int> h_ctl;
+    DevBuf<float> io_f;        // host-API staging
+    DevBuf<long long> io_l;
+    DevBuf<unsigned long long> io_u;
+    DevBuf<unsigned long long> assign_best;
+
+    size_t pool_budget_bytes = (size_t)1 << 30;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    SearchStats stats;
+    int num_sms = 148;
+
+    IvfIndex(int d, long nlist, int metric, int device);
+    ~IvfIndex();
+
+    // centroids are HOST pointers here
+    void set_centroids(const float* c, bool compute_interdis);
+    void get_centroids(float* out) const;
+    void get_interdis(float* out) const;
+    void set_interdis(const float* in);
+
+    // x: device pointer n x d (row stride d); list_no/ids: host (nullable)
+    void add_device(long n, const float* x_dev, const long long* ids_host, const long long* list_no_host);
+    void assign_device(long n, const float* x_dev, long long* list_no_host);
+    void reset();
+    void gather_rows(const long long* rows_host, long m, float* out_host);
+
+    void set_error_model(int arcos_size, int n_traces, const long* trace_off, const float* phi,
+                         const float* U, const float* sigma, float multipler, float std_m);
+
+    // coarse: ranks all nlist centroids for n staged queries (x_dev n x d) into c_dis/c_keys
+    void coarse_rank(long n, const float* x_dev);
+    void search(const QueryBatch& qb);
+    int max_num() const { return (int)(nlist / 8 + 20); }
+    int expected_traces() const { int t = 0; for (long p = 1; p <= nlist / 8; p <<= 1) t++; return t; }
+    ErrModelView model_view() const;
+};
+
+// ---- kernels' host launchers (one per .cu) ----
+void launch_pad_rows(const float* src, long n, int d, float* dst, int dpad, cudaStream_t s);
+void launch_coarse_distances(int metric, const float* xq, long nq, const float* cent, long nlist,
+                             int dpad, float* out_dis /*nq x nlist or null*/,
+                             unsigned long long* out_best /*nq or null*/, cudaStream_t s);
+void launch_rank_rows(int metric, const float* dis, long nq, long nlist, float* out_dis, int* out_keys,
+                      cudaStream_t s);
+void launch_interdis(int metric, const float* cent, long nlist, int dpad, float* out, cudaStream_t s);
+void launch_merge_tables(int metric, long n, long k, long nshard, const float* all_D,
+                         const long long* all_I, const long long* translations, float* D,
+                         long long* I, cudaStream_t s);
+
+}  // namespace auncel

@@ -1,0 +1,467 @@
+// IvfIndex: the device-resident IndexIVFFlat and the host side of the query path.
+#include <algorithm>
+#include <cstring>
+
+#include "merge.cuh"
+
+namespace auncel {
+
+IvfIndex::IvfIndex(int d_, long nlist_, int metric_, int device_)
+    : d(d_), dpad((d_ + 3) / 4 * 4), nlist(nlist_), metric(metric_), device(device_) {
+    AUNCEL_CHECK(d > 0 && nlist > 0, "d and nlist must be positive");
+    AUNCEL_CHECK(metric == METRIC_L2 || metric == METRIC_IP, "metric must be 0 (IP) or 1 (L2)");
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    num_sms = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreate(&ev0));
+    CUDA_CHECK(cudaEventCreate(&ev1));
+    h_list_off.assign(nlist + 1, 0);
+    list_off.ensure(nlist + 1);
+    CUDA_CHECK(cudaMemset(list_off.p, 0, (nlist + 1) * sizeof(long long)));
+    ctl.ensure(CTL_SIZE + 8);
+    h_ctl.ensure(CTL_SIZE + 8);
+    // arccos LUT: error_pro::construct_arcos, IVF_pro.cpp:151-160 (host libm, like the reference)
+    int len = 500;
+    h_arcos.resize(len);
+    float sc = len / 2;
+    for (int i = 0; i < len; i++) h_arcos[i] = std::acos(float(i - sc) / sc);
+    d_arcos.ensure(len);
+    CUDA_CHECK(cudaMemcpy(d_arcos.p, h_arcos.data(), len * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+IvfIndex::~IvfIndex() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamDestroy(stream);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+}
+
+void IvfIndex::set_centroids(const float* c, bool compute_interdis) {
+    CUDA_CHECK(cudaSetDevice(device));
+    io_f.ensure((size_t)nlist * d);
+    CUDA_CHECK(cudaMemcpyAsync(io_f.p, c, (size_t)nlist * d * sizeof(float), cudaMemcpyHostToDevice, stream));
+    centroids.ensure((size_t)nlist * dpad);
+    launch_pad_rows(io_f.p, nlist, d, centroids.p, dpad, stream);
+    trained = true;
+    have_interdis = false;
+    if (compute_interdis) {
+        // Level1Quantizer::train_q1's Auncel part, IndexIVF.cpp:97-109.
+        size_t tri = (size_t)nlist * (nlist - 1) / 2;
+        interdis.ensure(std::max<size_t>(tri, 1));
+        if (metric == METRIC_L2) {
+            launch_interdis(metric, centroids.p, nlist, dpad, interdis.p, stream);
+        } else {
+            // The reference rescales centroid 0 by its own norm nlist times (the loop never
+            // advances `st`, :102-107) and then takes acos of the inner products with libm.
+            // Same here: host rescale of row 0, device inner products, host std::acos.
+            std::vector<float> c0(c, c + d);
+            for (long i = 0; i < nlist; i++) {
+                float s[4] = {0, 0, 0, 0};
+                int j = 0;
+                for (; j + 4 <= d; j += 4)
+                    for (int l = 0; l < 4; l++) s[l] = fadd(s[l], fmul(c0[j + l], c0[j + l]));
+                for (int l = 0; l < 4; l++) {
+                    float v = j + l < d ? c0[j + l] : 0.f;
+                    s[l] = fadd(s[l], fmul(v, v));
+                }
+                float norm = sqrtf(fadd(fadd(s[0], s[1]), fadd(s[2], s[3])));
+                for (int jj = 0; jj < d; jj++) c0[jj] = fdiv(c0[jj], norm);
+            }
+            DevBuf<float> tmp;
+            tmp.ensure((size_t)nlist * dpad);
+            CUDA_CHECK(cudaMemcpyAsync(tmp.p, centroids.p, (size_t)nlist * dpad * sizeof(float),
+                                       cudaMemcpyDeviceToDevice, stream));
+            std::vector<float> row0(dpad, 0.f);
+            std::copy(c0.begin(), c0.end(), row0.begin());
+            CUDA_CHECK(cudaMemcpyAsync(tmp.p, row0.data(), dpad * sizeof(float), cudaMemcpyHostToDevice, stream));
+            launch_interdis(metric, tmp.p, nlist, dpad, interdis.p, stream);
+            std::vector<float> h(tri);
+            CUDA_CHECK(cudaMemcpyAsync(h.data(), interdis.p, tri * sizeof(float), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaStreamSynchronize(stream));
+            for (size_t i = 0; i < tri; i++) h[i] = std::acos(h[i]);
+            CUDA_CHECK(cudaMemcpyAsync(interdis.p, h.data(), tri * sizeof(float), cudaMemcpyHostToDevice, stream));
+        }
+        have_interdis = true;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+void IvfIndex::get_centroids(float* out) const {
+    CUDA_CHECK(cudaSetDevice(device));
+    AUNCEL_CHECK(trained, "index has no centroids");
+    CUDA_CHECK(cudaMemcpy2D(out, d * sizeof(float), centroids.p, dpad * sizeof(float), d * sizeof(float), nlist,
+                            cudaMemcpyDeviceToHost));
+}
+
+void IvfIndex::get_interdis(float* out) const {
+    CUDA_CHECK(cudaSetDevice(device));
+    AUNCEL_CHECK(have_interdis, "interdis_cem was not computed");
+    CUDA_CHECK(cudaMemcpy(out, interdis.p, (size_t)nlist * (nlist - 1) / 2 * sizeof(float), cudaMemcpyDeviceToHost));
+}
+
+void IvfIndex::set_interdis(const float* in) {
+    CUDA_CHECK(cudaSetDevice(device));
+    size_t tri = (size_t)nlist * (nlist - 1) / 2;
+    interdis.ensure(std::max<size_t>(tri, 1));
+    CUDA_CHECK(cudaMemcpy(interdis.p, in, tri * sizeof(float), cudaMemcpyHostToDevice));
+    have_interdis = true;
+}
+
+void IvfIndex::reset() {
+    ntotal = 0;
+    std::fill(h_list_off.begin(), h_list_off.end(), 0);
+    CUDA_CHECK(cudaSetDevice(device));
+    CUDA_CHECK(cudaMemset(list_off.p, 0, (nlist + 1) * sizeof(long long)));
+}
+
+// quantizer->assign (Index.cpp:42-47): k = 1 search; first strictly-best centroid wins.
+void IvfIndex::assign_device(long n, const float* x_dev, long long* list_no_host) {
+    CUDA_CHECK(cudaSetDevice(device));
+    AUNCEL_CHECK(trained, "index is not trained");
+    const long chunk = 1 << 20;
+    q_x.ensure((size_t)std::min(n, chunk) * dpad);
+    assign_best.ensure(std::min(n, chunk));
+    std::vector<unsigned long long> h(std::min(n, chunk));
+    for (long i0 = 0; i0 < n; i0 += chunk) {
+        long m = std::min(chunk, n - i0);
+        const float* xs = x_dev + i0 * d;
+        if (dpad != d) {
+            launch_pad_rows(xs, m, d, q_x.p, dpad, stream);
+            xs = q_x.p;
+        }
+        for (long j0 = 0; j0 < m; j0 += 65535L * 64) {
+            long mm = std::min(65535L * 64, m - j0);
+            launch_coarse_distances(metric, xs + j0 * dpad, mm, centroids.p, nlist, dpad, nullptr,
+                                    assign_best.p + j0, stream);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(h.data(), assign_best.p, m * sizeof(unsigned long long),
+                                   cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        for (long i = 0; i < m; i++) list_no_host[i0 + i] = (long long)(h[i] & 0xffffffffull);
+    }
+}
+
+__global__ void scatter_rows_kernel(const float* __restrict__ src, int d, const long long* __restrict__ dst_row,
+                                    long n, float* __restrict__ dst, int dpad) {
+    // one warp per row
+    long r = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    long long o = dst_row[r];
+    if (o < 0) return;
+    for (int c = lane; c < dpad; c += 32) dst[o * dpad + c] = c < d ? src[r * (long)d + c] : 0.f;
+}
+
+__global__ void scatter_ids_kernel(const long long* __restrict__ ids, const long long* __restrict__ dst_row, long n,
+                                   long long* __restrict__ dst) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long o = dst_row[i];
+    if (o >= 0) dst[o] = ids[i];
+}
+
+__global__ void move_lists_kernel(const float* __restrict__ old_codes, const long long* __restrict__ old_ids,
+                                  const long long* __restrict__ old_off, const long long* __restrict__ new_off,
+                                  long nlist, int dpad, float* __restrict__ codes, long long* __restrict__ ids) {
+    // one CTA per list: copy the existing prefix of every list to its new place
+    long l = blockIdx.x;
+    long long o0 = old_off[l], cnt = old_off[l + 1] - o0, n0 = new_off[l];
+    long long words = cnt * dpad;
+    for (long long i = threadIdx.x; i < words; i += blockDim.x) codes[n0 * dpad + i] = old_codes[o0 * dpad + i];
+    for (long long i = threadIdx.x; i < cnt; i += blockDim.x) ids[n0 + i] = old_ids[o0 + i];
+}
+
+// IndexIVFFlat::add_core (IndexIVFFlat.cpp:41-80): every vector is appended to the list of
+// its nearest centroid, in input order (the in-list order matters at distance ties).  Lists
+// live in one arena in list order, so an add rebuilds the arena: old prefix + new suffix.
+void IvfIndex::add_device(long n, const float* x_dev, const long long* ids_host, const long long* list_no_host) {
+    CUDA_CHECK(cudaSetDevice(device));
+    AUNCEL_CHECK(trained, "index is not trained");
+    if (n == 0) return;
+    std::vector<long long> ln;
+    if (!list_no_host) {
+        ln.resize(n);
+        assign_device(n, x_dev, ln.data());
+        list_no_host = ln.data();
+    }
+    // stable counting sort on the host: destination row of every new vector
+    std::vector<long long> add_cnt(nlist, 0);
+    long nadd = 0;
+    for (long i = 0; i < n; i++) {
+        long long l = list_no_host[i];
+        if (l < 0) continue;  // IndexIVFFlat.cpp:65-66
+        AUNCEL_CHECK(l < nlist, "list number out of range");
+        add_cnt[l]++;
+        nadd++;
+    }
+    std::vector<long long> new_off(nlist + 1, 0);
+    for (long l = 0; l < nlist; l++)
+        new_off[l + 1] = new_off[l] + (h_list_off[l + 1] - h_list_off[l]) + add_cnt[l];
+    std::vector<long long> cursor(nlist);
+    for (long l = 0; l < nlist; l++) cursor[l] = new_off[l] + (h_list_off[l + 1] - h_list_off[l]);
+    std::vector<long long> dst_row(n), idv(n);
+    for (long i = 0; i < n; i++) {
+        long long l = list_no_host[i];
+        dst_row[i] = l < 0 ? -1 : cursor[l]++;
+        idv[i] = ids_host ? ids_host[i] : ntotal + i;  // IndexIVFFlat.cpp:62
+    }
+    long long new_total = new_off[nlist];
+    DevBuf<float> ncodes;
+    DevBuf<long long> nids, d_new_off, d_dst, d_ids;
+    ncodes.ensure(std::max<size_t>((size_t)new_total * dpad, 4));
+    nids.ensure(std::max<size_t>(new_total, 1));
+    d_new_off.ensure(nlist + 1);
+    d_dst.ensure(n);
+    d_ids.ensure(n);
+    CUDA_CHECK(cudaMemcpyAsync(d_new_off.p, new_off.data(), (nlist + 1) * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    CUDA_CHECK(cudaMemcpyAsync(d_dst.p, dst_row.data(), n * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    CUDA_CHECK(cudaMemcpyAsync(d_ids.p, idv.data(), n * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    if (h_list_off[nlist] > 0)
+        move_lists_kernel<<<(unsigned)nlist, 256, 0, stream>>>(codes.p, ids.p, list_off.p, d_new_off.p, nlist, dpad,
+                                                             ncodes.p, nids.p);
+    scatter_rows_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(x_dev, d, d_dst.p, n, ncodes.p, dpad);
+    scatter_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_ids.p, d_dst.p, n, nids.p);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(list_off.p, d_new_off.p, (nlist + 1) * sizeof(long long), cudaMemcpyDeviceToDevice, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    std::swap(codes.p, ncodes.p);
+    std::swap(codes.cap, ncodes.cap);
+    std::swap(ids.p, nids.p);
+    std::swap(ids.cap, nids.cap);
+    h_list_off = new_off;
+    ntotal += n;  // the reference counts skipped (-1) vectors too, IndexIVFFlat.cpp:79
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ codes, int dpad, int d,
+                                   const long long* __restrict__ rows, long m, float* __restrict__ out) {
+    long r = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (r >= m) return;
+    const float* src = codes + rows[r] * dpad;
+    for (int c = lane; c < d; c += 32) out[r * (long)d + c] = src[c];
+}
+
+// rows of the arena (arena row numbers, host) -> compact m x d host matrix
+void IvfIndex::gather_rows(const long long* rows_host, long m, float* out_host) {
+    CUDA_CHECK(cudaSetDevice(device));
+    if (m == 0) return;
+    DevBuf<long long> r;
+    DevBuf<float> o;
+    const long chunk = 1L << 22;
+    r.ensure(std::min(m, chunk));
+    o.ensure((size_t)std::min(m, chunk) * d);
+    for (long i0 = 0; i0 < m; i0 += chunk) {
+        long mm = std::min(chunk, m - i0);
+        CUDA_CHECK(cudaMemcpyAsync(r.p, rows_host + i0, mm * sizeof(long long), cudaMemcpyHostToDevice, stream));
+        gather_rows_kernel<<<(unsigned)((mm * 32 + 255) / 256), 256, 0, stream>>>(codes.p, dpad, d, r.p, mm, o.p);
+        CUDA_CHECK(cudaMemcpyAsync(out_host + (size_t)i0 * d, o.p, (size_t)mm * d * sizeof(float),
+                                   cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+}
+
+void IvfIndex::set_error_model(int arcos_size, int ntr, const long* trace_off, const float* phi,
+                               const float* U, const float* sigma, float mult, float sm) {
+    CUDA_CHECK(cudaSetDevice(device));
+    AUNCEL_CHECK(arcos_size == (int)h_arcos.size(), "arccos table size must be 500 (IVF_pro.h:86)");
+    AUNCEL_CHECK(ntr == expected_traces(), "need one trace per power of two <= nlist/8 (IndexIVF.cpp:209-221)");
+    for (int t = 0; t < ntr; t++)
+        AUNCEL_CHECK(trace_off[t + 1] > trace_off[t], "every trace needs at least one (phi,U) bucket");
+    n_traces = ntr;
+    h_trace_off.assign(trace_off, trace_off + ntr + 1);
+    long tot = trace_off[ntr];
+    h_phi.assign(phi, phi + tot);
+    h_U.assign(U, U + tot);
+    h_sigma.assign(sigma, sigma + tot);
+    d_trace_off.ensure(ntr + 1);
+    d_phi.ensure(tot);
+    d_U.ensure(tot);
+    d_sigma.ensure(tot);
+    CUDA_CHECK(cudaMemcpy(d_trace_off.p, h_trace_off.data(), (ntr + 1) * sizeof(long), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(d_phi.p, h_phi.data(), tot * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(d_U.p, h_U.data(), tot * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(d_sigma.p, h_sigma.data(), tot * sizeof(float), cudaMemcpyHostToDevice));
+    multipler = mult;
+    std_m = sm;
+}
+
+ErrModelView IvfIndex::model_view() const {
+    ErrModelView m;
+    m.arcos = d_arcos.p;
+    m.arcos_size = (int)h_arcos.size();
+    m.n_traces = n_traces;
+    m.trace_off = d_trace_off.p;
+    m.phi = d_phi.p;
+    m.U = d_U.p;
+    m.sigma = d_sigma.p;
+    m.std_m = std_m;
+    m.multipler = multipler;
+    return m;
+}
+
+// IndexFlat::search with k = nlist (IndexFlat.cpp:42-56): all centroids, best first.
+void IvfIndex::coarse_rank(long n, const float* xs /* n x dpad, device */) {
+    c_dis.ensure((size_t)n * nlist);
+    c_keys.ensure((size_t)n * nlist);
+    DevBuf<float>& raw = c_raw;
+    const long chunk = 65535L * 64;
+    raw.ensure((size_t)std::min(n, chunk) * nlist);
+    for (long i0 = 0; i0 < n; i0 += chunk) {
+        long m = std::min(chunk, n - i0);
+        launch_coarse_distances(metric, xs + i0 * dpad, m, centroids.p, nlist, dpad, raw.p, nullptr, stream);
+        launch_rank_rows(metric, raw.p, m, nlist, c_dis.p + i0 * nlist, c_keys.p + i0 * nlist, stream);
+    }
+}
+
+// IndexIVF::search -> search_preassigned (IndexIVF.cpp:335-736) for a batch of device-resident
+// queries.  Rounds: [r0, r0+w) probe ranks per active query -> plan (group pairs by list) ->
+// scan (fused selection) -> merge + termination check -> compact the active list.
+void IvfIndex::search(const QueryBatch& qb) {
+    CUDA_CHECK(cudaSetDevice(device));
+    AUNCEL_CHECK(trained, "index is not trained");
+    AUNCEL_CHECK(qb.k >= 1 && qb.k <= MAX_K, "k must be in [1, 128]");
+    AUNCEL_CHECK(qb.nprobe >= 1, "nprobe must be >= 1");
+    const long n = qb.n;
+    if (n == 0) return;
+    AUNCEL_CHECK(n < (1L << 31), "too many queries in one call");
+    const int K = qb.k;
+    const int nprobe = (int)std::min<long>(qb.nprobe, nlist);
+    if (qb.mode != 0) {
+        AUNCEL_CHECK(have_interdis, "tuned search needs interdis_cem (train/set_centroids in tune mode)");
+        AUNCEL_CHECK(nprobe == nlist, "Auncel search ranks all centroids: nprobe must equal nlist (profile.cpp:218)");
+        AUNCEL_CHECK(nlist >= 16, "nlist too small for the error model");
+    }
+    if (qb.mode == 1) {
+        AUNCEL_CHECK(n_traces > 0, "Search tune start can't start without IVF_pro init and training");
+        AUNCEL_CHECK(qb.query_topk >= 1 && qb.query_topk <= K, "query_topk must be in [1, max_topk]");
+        AUNCEL_CHECK(qb.require_acc != nullptr, "require_acc missing");
+    }
+    stats = SearchStats();
+    CUDA_CHECK(cudaEventRecord(ev0, stream));
+
+    // ---- stage queries (pad rows), coarse ranking
+    const float* xs = qb.x;
+    if (dpad != d) {
+        q_x.ensure((size_t)n * dpad);
+        launch_pad_rows(qb.x, n, d, q_x.p, dpad, stream);
+        xs = q_x.p;
+    }
+    coarse_rank(n, xs);
+    CUDA_CHECK(cudaMemsetAsync(ctl.p, 0, (CTL_SIZE + 8) * sizeof(int), stream));
+
+    // ---- per-query state
+    state.ensure(QState::bytes(n, K));
+    RoundParams rp;
+    rp.codes = codes.p;
+    rp.list_off = list_off.p;
+    rp.ids = ids.p;
+    rp.dpad = dpad;
+    rp.nlist = nlist;
+    rp.metric = metric;
+    rp.xq = xs;
+    rp.ckeys = c_keys.p;
+    rp.cdis = c_dis.p;
+    rp.n = n;
+    rp.K = K;
+    rp.st.carve(state.p, n, K);
+    rp.ctl = ctl.p;
+    rp.list_cnt = list_cnt.ensure(nlist);
+    rp.list_pair_off = list_pair_off.ensure(nlist + 1);
+    rp.list_tile_off = list_tile_off.ensure(nlist + 1);
+    rp.list_cursor = list_cursor.ensure(nlist);
+    active.ensure(n);
+    active2.ensure(n);
+
+    TuneParams tp;
+    tp.mode = qb.mode;
+    tp.query_topk = qb.query_topk;
+    tp.profile = qb.profile;
+    tp.overhead_profile = qb.overhead_profile;
+    tp.nprobe = nprobe;
+    tp.max_codes = qb.max_codes;
+    tp.model = model_view();
+    tp.require_acc = qb.require_acc;
+    tp.gt_kth = qb.gt_kth;
+    tp.t_recalls = qb.t_recalls;
+    tp.dtb = nullptr;
+    tp.max_num = max_num();
+    tp.snapshots = qb.snapshots;
+    tp.n_traces = expected_traces();
+    if (qb.mode != 0) {
+        float* dtb_p = qb.dtb_out ? qb.dtb_out : dtb.ensure((size_t)n * tp.max_num);
+        launch_set_online(metric, nlist, n, c_dis.p, c_keys.p, interdis.p, d_arcos.p, (int)h_arcos.size(), dtb_p,
+                          tp.max_num, ctl.p, stream);
+        tp.dtb = dtb_p;
+    }
+    launch_init_state(rp, tp, qb.mode == 1 ? qb.my_nprobe : nullptr, active.p, stream);
+
+    // ---- rounds
+    int n_active = (int)n;
+    int r0 = 0;
+    int* act_cur = active.p;
+    int* act_nxt = active2.p;
+    const int max_stage = qb.mode == 2 ? (int)std::min<long>(nprobe, nlist / 8 + 1) : nprobe;
+    const size_t pool_entries = std::max<size_t>(pool_budget_bytes / 8, (size_t)K);
+    float scan_ms_total = 0.f;
+    while (n_active > 0 && r0 < max_stage) {
+        // window: fixed/calibration scans as wide as the pool allows; the error-bounded search
+        // doubles its window (1,1,2,4,...) so undecided queries never speculate far past their
+        // stop stage (with multipler >= 2 every speculative list is needed anyway).
+        long w_cap = (long)(pool_entries / ((size_t)n_active * K));
+        w_cap = std::max(1L, std::min<long>(w_cap, 1024));
+        long w = max_stage - r0;
+        if (qb.mode == 1 && !qb.overhead_profile) w = std::min<long>(w, std::max(1, r0));
+        w = std::min(w, w_cap);
+        // segments: split lists when there are too few (list, query-tile) units to fill the GPU
+        long est_tiles = std::min<long>((long)n_active * w, nlist) + (long)n_active * w / SCAN_QT;
+        long S = (2L * num_sms + est_tiles - 1) / est_tiles;
+        S = std::max(1L, std::min<long>(S, 32));
+        while (S > 1 && (size_t)n_active * w * S * K > pool_entries) S--;
+        rp.active = act_cur;
+        rp.n_active = n_active;
+        rp.r0 = r0;
+        rp.w = (int)w;
+        rp.S = (int)S;
+        size_t slots = (size_t)n_active * w * S;
+        pool.ensure(slots * K * 8);
+        rp.cand_d = reinterpret_cast<float*>(pool.p);
+        rp.cand_off = reinterpret_cast<unsigned*>(pool.p + slots * K * 4);
+        rp.slot_cnt = slot_cnt.ensure(slots);
+        rp.pairs = pairs.ensure((size_t)n_active * w);
+
+        launch_plan(rp, stream);
+        launch_scan(rp, num_sms, stream);
+        launch_merge_check(rp, tp, stream);
+        launch_compact_active(rp, r0 + (int)w, act_nxt, h_ctl.p, stream);
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        n_active = h_ctl.p[CTL_N_ACTIVE];
+        stats.rounds++;
+        stats.scan_tiles += (uint64_t)h_ctl.p[CTL_TOTAL_TILES];
+        stats.scan_pairs += (uint64_t)h_ctl.p[CTL_TOTAL_PAIRS];
+        std::swap(act_cur, act_nxt);
+        r0 += (int)w;
+    }
+
+    // ---- results
+    DevBuf<unsigned long long>& st_dev = io_u;
+    st_dev.ensure(4);
+    CUDA_CHECK(cudaMemsetAsync(st_dev.p, 0, 4 * sizeof(unsigned long long), stream));
+    launch_finalize(rp, tp, qb.D, qb.I, qb.my_nprobe, st_dev.p, stream);
+    unsigned long long h_st[2];
+    CUDA_CHECK(cudaMemcpyAsync(h_st, st_dev.p, sizeof(h_st), cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaMemcpyAsync(h_ctl.p, ctl.p, CTL_SIZE * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaEventRecord(ev1, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+    stats.nq = n;
+    stats.nlist = h_st[0];
+    stats.ndis = h_st[1];
+    stats.search_ms = ms;
+    stats.scan_ms = scan_ms_total;
+    stats.err_bits = (uint64_t)h_ctl.p[CTL_ERR];
+}
+
+}  // namespace auncel

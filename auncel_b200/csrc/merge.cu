@@ -1,0 +1,369 @@
+// Subsystems (3) + (4): per-query running top-k and Auncel's termination check, on device.
+//
+// merge_check_kernel replays, for every active query, the sequential part of
+// IndexIVF::search_preassigned (/root/reference/Auncel/IndexIVF.cpp:526-675): after the
+// candidates of probe rank `stage` are merged into the running sorted top-k, the tune block
+// (:551-638) is evaluated exactly as the reference does -- sorted copy of the heap
+// (IP: arccos LUT first), cur_num (IVF_pro.cpp:258-291), the plateau counter, my_nprobe =
+// stage * multipler, the break rule -- or, in calibration mode, the top-k snapshot of the
+// power-of-two stages (:640-673) is emitted.  The decision is a pure function of the sorted
+// top-k after each stage, so merging per-(query, list) partial results in probe order
+// reproduces the reference's heap walk (tests/test_lowlevel_ivf.cpp:426-557 invariant).
+#include "merge.cuh"
+
+namespace auncel {
+
+__device__ __forceinline__ float neutral(int metric) { return metric == METRIC_L2 ? FLT_MAX : -FLT_MAX; }
+
+// --------------------------------------------------------------------------- init
+__global__ void init_state_kernel(RoundParams rp, TuneParams tp, const unsigned long long* mynp_in,
+                                  int* active_out) {
+    long q = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (q >= rp.n) return;
+    int limit = tp.nprobe, cut = 0;
+    if (tp.max_codes > 0) {  // IndexIVF.cpp:541-543
+        long cum = 0;
+        for (int p = 0; p < tp.nprobe; p++) {
+            int l = rp.ckeys[q * rp.nlist + p];
+            cum += rp.list_off[l + 1] - rp.list_off[l];
+            if (cum >= tp.max_codes) {
+                limit = p + 1;
+                cut = 1;
+                break;
+            }
+        }
+    }
+    int bound = limit, decided = 0;
+    unsigned long long mynp = 0;
+    const long n8 = rp.nlist / 8;
+    if (tp.mode == 2) {
+        bound = (int)min((long)limit, n8 + 1);  // scans one list past nlist/8, then breaks (:643)
+    } else if (tp.mode == 1) {
+        if (tp.overhead_profile) {
+            bound = (int)min((long)limit, max(1L, n8));  // :633-636
+            decided = 1;
+        } else {
+            mynp = mynp_in ? mynp_in[q] : 0ull;
+            if (mynp != 0) {  // stale decision from an earlier call is replayed (:627-632)
+                unsigned long long b = mynp < (unsigned long long)limit ? mynp : (unsigned long long)limit;
+                bound = (int)b;
+                decided = 1;
+            }
+        }
+    }
+    rp.st.limit[q] = limit;
+    rp.st.cut[q] = cut;
+    rp.st.bound[q] = bound;
+    rp.st.decided[q] = decided;
+    rp.st.rcnt[q] = 0;
+    rp.st.tau[q] = neutral(rp.metric);
+    rp.st.stoped[q] = 0;
+    rp.st.pre_val[q] = 0.f;
+    rp.st.mynp[q] = mynp;
+    active_out[q] = (int)q;
+}
+
+void launch_init_state(const RoundParams& rp, const TuneParams& tp, const unsigned long long* mynp_in,
+                       int* active_out, cudaStream_t s) {
+    if (rp.n == 0) return;
+    init_state_kernel<<<(unsigned)((rp.n + 127) / 128), 128, 0, s>>>(rp, tp, mynp_in, active_out);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// --------------------------------------------------------------------------- set_online
+// error_pro::set_online, IVF_pro.cpp:196-238: one warp per query.
+__global__ void set_online_kernel(int metric, long nlist, long n, const float* __restrict__ cdis,
+                                  const int* __restrict__ ckeys, const float* __restrict__ interdis,
+                                  const float* __restrict__ arcos, int arcos_size, float* __restrict__ dtb,
+                                  int max_num, int* ctl) {
+    long q = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (q >= n) return;
+    const float* cd = cdis + q * nlist;
+    const int* ci = ckeys + q * nlist;
+    int err = 0;
+    const int cur = ci[0];
+    float a = cd[0];
+    if (metric == METRIC_IP) a = arcos_lookup(arcos, arcos_size, a, &err);
+    for (int k = lane; k < max_num; k += 32) {
+        float out = 0.f;  // dtb[max_num-1] is never written by the reference (stays 0)
+        if (k < max_num - 1 && k + 1 < nlist) {
+            float c2c = interdis[tri_index((size_t)nlist, (size_t)cur, (size_t)ci[k + 1])];
+            float b = cd[k + 1];
+            if (metric == METRIC_IP) b = arcos_lookup(arcos, arcos_size, b, &err);
+            out = cosine_theorem(a, b, c2c, &err);
+        }
+        dtb[q * max_num + k] = out;
+    }
+    if (err) atomicOr(&ctl[CTL_ERR], err);
+}
+
+void launch_set_online(int metric, long nlist, long n, const float* cdis, const int* ckeys,
+                       const float* interdis, const float* arcos, int arcos_size, float* dtb,
+                       int max_num, int* ctl, cudaStream_t s) {
+    if (n == 0) return;
+    set_online_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, s>>>(metric, nlist, n, cdis, ckeys, interdis,
+                                                                      arcos, arcos_size, dtb, max_num, ctl);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// --------------------------------------------------------------------------- merge + check
+constexpr int MC_WARPS = 4;
+
+template <int KP>
+struct MergeSmem {
+    unsigned long long key[2 * KP];
+    unsigned long long code[2][KP];
+    unsigned long long ccode[KP];
+    float Rd[KP];
+    float ang[KP];
+};
+
+template <int KP>
+__global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams rp, TuneParams tp) {
+    __shared__ MergeSmem<KP> sm_all[MC_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a = blockIdx.x * MC_WARPS + warp;
+    if (a >= rp.n_active) return;
+    MergeSmem<KP>& sm = sm_all[warp];
+    const int q = rp.active[a];
+    const int K = rp.K, metric = rp.metric;
+    const float neut = neutral(metric);
+
+    int rcnt = rp.st.rcnt[q];
+    int bound = rp.st.bound[q], decided = rp.st.decided[q];
+    const int limit = rp.st.limit[q], cut = rp.st.cut[q];
+    int stoped = rp.st.stoped[q];
+    float pre_val = rp.st.pre_val[q];
+    unsigned long long mynp = rp.st.mynp[q];
+    int cur = 0;  // code ping-pong
+    int err = 0;
+
+    for (int i = lane; i < KP; i += 32) {
+        sm.Rd[i] = i < rcnt ? rp.st.Rd[(long)q * K + i] : neut;
+        sm.code[0][i] = i < rcnt ? rp.st.Rcode[(long)q * K + i] : 0ull;
+    }
+    __syncwarp();
+
+    const float* dtb = tp.dtb ? tp.dtb + (long)q * tp.max_num : nullptr;
+
+    for (int p_rel = 0; p_rel < rp.w; p_rel++) {
+        const int stage = rp.r0 + p_rel + 1;
+        if (stage > bound) break;
+        // ---- merge the candidates of probe rank stage-1 (all segments)
+        for (int seg = 0; seg < rp.S; seg++) {
+            const long slot = ((long)a * rp.w + p_rel) * rp.S + seg;
+            const int c = rp.slot_cnt[slot];
+            if (c == 0) continue;
+            for (int i = lane; i < KP; i += 32) {
+                unsigned long long k1 = ~0ull, k2 = ~0ull;
+                if (i < rcnt) {
+                    uint32_t o = f2ord(sm.Rd[i]);
+                    if (metric == METRIC_IP) o = ~o;
+                    k1 = ((unsigned long long)o << 32) | (unsigned)i;
+                }
+                if (i < c) {
+                    uint32_t o = f2ord(rp.cand_d[slot * K + i]);
+                    if (metric == METRIC_IP) o = ~o;
+                    k2 = ((unsigned long long)o << 32) | (unsigned)(KP + i);
+                    sm.ccode[i] = ((unsigned long long)(unsigned)(stage - 1) << 32) | rp.cand_off[slot * K + i];
+                }
+                sm.key[i] = k1;
+                sm.key[2 * KP - 1 - i] = k2;
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int stride = KP; stride > 0; stride >>= 1) {
+                for (int t = lane; t < KP; t += 32) {
+                    int lo = 2 * t - (t & (stride - 1));
+                    int hi = lo + stride;
+                    unsigned long long x = sm.key[lo], y = sm.key[hi];
+                    if (x > y) {
+                        sm.key[lo] = y;
+                        sm.key[hi] = x;
+                    }
+                }
+                __syncwarp();
+            }
+            rcnt = min(K, rcnt + c);
+            for (int i = lane; i < KP; i += 32) {
+                if (i < rcnt) {
+                    unsigned long long k = sm.key[i];
+                    uint32_t o = (uint32_t)(k >> 32);
+                    if (metric == METRIC_IP) o = ~o;
+                    unsigned idx = (unsigned)(k & 0xffffffffu);
+                    sm.Rd[i] = ord2f(o);
+                    sm.code[cur ^ 1][i] = idx < (unsigned)KP ? sm.code[cur][idx] : sm.ccode[idx - KP];
+                } else {
+                    sm.Rd[i] = neut;
+                }
+            }
+            cur ^= 1;
+            __syncwarp();
+        }
+
+        const bool cut_here = cut && stage == limit;  // max_codes break precedes both blocks (:541)
+        if (cut_here) break;
+
+        if (tp.mode == 1 && !tp.overhead_profile) {
+            if (!decided) {
+                // ---- tune block, IndexIVF.cpp:551-626
+                const float* S = sm.Rd;
+                if (metric == METRIC_IP) {
+                    for (int i = lane; i < K; i += 32)
+                        sm.ang[i] = arcos_lookup(tp.model.arcos, tp.model.arcos_size, sm.Rd[i], &err);
+                    __syncwarp();
+                    S = sm.ang;
+                }
+                const int ind = stage_to_ind((size_t)stage, (size_t)rp.nlist);
+                const unsigned qk = (unsigned)tp.query_topk;
+                const unsigned pre = cur_num(tp.model, S, dtb, ind, qk, &err);
+                float recall = fdiv((float)pre, (float)qk);
+                const float ext = rcnt == K ? sm.Rd[K - 1] : neut;  // heap extreme (:573-587)
+                const float req = tp.require_acc[q];
+                const unsigned long long stops = (unsigned long long)fmul(req, 12.f);
+                if (stage > 1) {
+                    stoped = (ext == pre_val) ? stoped + 1 : 0;
+                    if ((unsigned long long)stoped >= stops) recall = 1.f;
+                }
+                pre_val = ext;
+                if ((recall >= req && mynp == 0) || (stage >= rp.nlist / 8 && mynp == 0)) {
+                    mynp = (unsigned long long)fmul((float)stage, tp.model.multipler);
+                    if (mynp >= (unsigned long long)rp.nlist && tp.t_recalls && lane == 0) tp.t_recalls[q] = 1.f;
+                }
+                if (mynp != 0) {
+                    decided = 1;
+                    unsigned long long b = mynp > (unsigned long long)stage ? mynp : (unsigned long long)stage;
+                    bound = (int)(b < (unsigned long long)limit ? b : (unsigned long long)limit);
+                }
+                __syncwarp();
+            }
+            if (decided && mynp != 0 && mynp <= (unsigned long long)stage) {
+                // the break of :627-632; with `profile` the true recall is logged first
+                if (tp.profile && tp.t_recalls && tp.gt_kth) {
+                    const float kd = tp.gt_kth[q];
+                    int cnt = 0;
+                    for (int i = lane; i < K; i += 32) {
+                        float v = sm.Rd[i];
+                        bool hit = metric == METRIC_L2 ? ((double)v <= dmul((double)kd, 1.0005))
+                                                       : ((double)v >= dmul((double)kd, 0.9995));
+                        cnt += hit ? 1 : 0;
+                    }
+                    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                    if (lane == 0) tp.t_recalls[q] = fdiv((float)cnt, (float)tp.query_topk);
+                }
+                bound = stage;
+                break;
+            }
+        } else if (tp.mode == 2) {
+            // ---- calibration snapshot, IndexIVF.cpp:640-655
+            if (stage <= rp.nlist / 8 && (stage & (stage - 1)) == 0) {
+                int ind = 0;
+                while ((1 << ind) != stage) ind++;
+                float* out = tp.snapshots + ((long)q * tp.n_traces + ind) * K;
+                for (int i = lane; i < K; i += 32) out[i] = sm.Rd[i];
+            }
+        }
+    }
+
+    // ---- write back
+    for (int i = lane; i < rcnt; i += 32) {
+        rp.st.Rd[(long)q * K + i] = sm.Rd[i];
+        rp.st.Rcode[(long)q * K + i] = sm.code[cur][i];
+    }
+    if (lane == 0) {
+        rp.st.rcnt[q] = rcnt;
+        rp.st.bound[q] = bound;
+        rp.st.decided[q] = decided;
+        rp.st.stoped[q] = stoped;
+        rp.st.pre_val[q] = pre_val;
+        rp.st.mynp[q] = mynp;
+        rp.st.tau[q] = rcnt == K ? sm.Rd[K - 1] : neut;
+        if (err) atomicOr(&rp.ctl[CTL_ERR], err);
+    }
+}
+
+void launch_merge_check(const RoundParams& rp, const TuneParams& tp, cudaStream_t s) {
+    if (rp.n_active == 0) return;
+    unsigned blocks = (unsigned)((rp.n_active + MC_WARPS - 1) / MC_WARPS);
+    if (rp.K <= 16) merge_check_kernel<16><<<blocks, MC_WARPS * 32, 0, s>>>(rp, tp);
+    else if (rp.K <= 32) merge_check_kernel<32><<<blocks, MC_WARPS * 32, 0, s>>>(rp, tp);
+    else if (rp.K <= 64) merge_check_kernel<64><<<blocks, MC_WARPS * 32, 0, s>>>(rp, tp);
+    else merge_check_kernel<128><<<blocks, MC_WARPS * 32, 0, s>>>(rp, tp);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// --------------------------------------------------------------------------- active list
+__global__ void compact_active_kernel(RoundParams rp, int r1, int* active_out) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= rp.n_active) return;
+    int q = rp.active[a];
+    if (rp.st.bound[q] > r1) {
+        int pos = atomicAdd(&rp.ctl[CTL_N_ACTIVE], 1);
+        active_out[pos] = q;
+    }
+}
+
+void launch_compact_active(const RoundParams& rp, int r1, int* active_out, int* h_ctl_pinned,
+                           cudaStream_t s) {
+    CUDA_CHECK(cudaMemsetAsync(rp.ctl + CTL_N_ACTIVE, 0, sizeof(int), s));
+    if (rp.n_active > 0) {
+        compact_active_kernel<<<(unsigned)((rp.n_active + 255) / 256), 256, 0, s>>>(rp, r1, active_out);
+        CUDA_CHECK(cudaGetLastError());
+    }
+    CUDA_CHECK(cudaMemcpyAsync(h_ctl_pinned, rp.ctl, CTL_SIZE * sizeof(int), cudaMemcpyDeviceToHost, s));
+}
+
+// --------------------------------------------------------------------------- finalize
+// heap_reorder output (Heap.h:295-322): best first, padded with neutral / -1; labels from the
+// inverted lists' id arrays; IndexIVFStats ndis / nlist (IndexIVF.cpp:676,731-734).
+__global__ void finalize_kernel(RoundParams rp, TuneParams tp, float* D, long long* I,
+                                unsigned long long* mynp_out, unsigned long long* stats) {
+    long q = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (q >= rp.n) return;
+    const int K = rp.K;
+    const int rcnt = rp.st.rcnt[q];
+    const float neut = neutral(rp.metric);
+    for (int i = lane; i < K; i += 32) {
+        float dv = neut;
+        long long id = -1;
+        if (i < rcnt) {
+            dv = rp.st.Rd[q * K + i];
+            unsigned long long code = rp.st.Rcode[q * K + i];
+            int p = (int)(code >> 32);
+            unsigned off = (unsigned)(code & 0xffffffffu);
+            int l = rp.ckeys[q * rp.nlist + p];
+            id = rp.ids[rp.list_off[l] + off];
+        }
+        D[q * K + i] = dv;
+        I[q * K + i] = id;
+    }
+    // stats: lists visited / codes scanned up to the stop stage
+    const int stop = rp.st.bound[q];
+    unsigned long long nd = 0, nl = 0;
+    for (int p = lane; p < stop; p += 32) {
+        int l = rp.ckeys[q * rp.nlist + p];
+        long long sz = rp.list_off[l + 1] - rp.list_off[l];
+        nd += (unsigned long long)sz;
+        nl += sz > 0 ? 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        nd += __shfl_xor_sync(0xffffffffu, nd, o);
+        nl += __shfl_xor_sync(0xffffffffu, nl, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&stats[0], nl);
+        atomicAdd(&stats[1], nd);
+        if (mynp_out && tp.mode == 1 && !tp.overhead_profile) mynp_out[q] = rp.st.mynp[q];
+    }
+}
+
+void launch_finalize(const RoundParams& rp, const TuneParams& tp, float* D, long long* I,
+                     unsigned long long* mynp_out, unsigned long long* stats_dev, cudaStream_t s) {
+    if (rp.n == 0) return;
+    finalize_kernel<<<(unsigned)((rp.n * 32 + 127) / 128), 128, 0, s>>>(rp, tp, D, I, mynp_out, stats_dev);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace auncel

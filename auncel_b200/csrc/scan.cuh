@@ -1,0 +1,79 @@
+// Shared declarations of the round pipeline (plan -> scan -> merge/check).
+#pragma once
+#include "engine.h"
+
+namespace auncel {
+
+// control block slots (device ints, mirrored to pinned host memory once per round)
+enum { CTL_N_ACTIVE = 0, CTL_TOTAL_TILES = 1, CTL_TILE_COUNTER = 2, CTL_TOTAL_PAIRS = 3,
+       CTL_ERR = 4, CTL_NLISTV_LO = 5, CTL_SIZE = 16 };
+
+// per-query running state, SoA, carved from IvfIndex::state
+struct QState {
+    int* limit;      // hard stage limit (nprobe / max_codes)
+    int* cut;        // 1: limit comes from max_codes (break before the tune block)
+    int* bound;      // current upper bound on stages to scan (== stop stage once decided)
+    int* decided;    // tune mode: my_nprobe fixed
+    int* rcnt;       // valid entries in R
+    float* tau;      // scan filter threshold (K-th best so far, or +-FLT_MAX)
+    int* stoped;     // plateau counter (IndexIVF.cpp:588-598)
+    float* pre_val;
+    unsigned long long* mynp;
+    float* Rd;                  // n x K   best-first distances
+    unsigned long long* Rcode;  // n x K   (probe rank << 32) | offset in list
+    static size_t bytes(long n, int K) {
+        return (size_t)n * (7 * 4 + 8 + 8 /*align slack*/) + (size_t)n * K * 12 + 256;
+    }
+    void carve(unsigned char* base, long n, int K) {
+        unsigned char* p = base;
+        auto take = [&](size_t b) { unsigned char* r = p; p += (b + 15) / 16 * 16; return r; };
+        Rcode = (unsigned long long*)take((size_t)n * K * 8);
+        mynp = (unsigned long long*)take((size_t)n * 8);
+        Rd = (float*)take((size_t)n * K * 4);
+        limit = (int*)take((size_t)n * 4);
+        cut = (int*)take((size_t)n * 4);
+        bound = (int*)take((size_t)n * 4);
+        decided = (int*)take((size_t)n * 4);
+        rcnt = (int*)take((size_t)n * 4);
+        tau = (float*)take((size_t)n * 4);
+        stoped = (int*)take((size_t)n * 4);
+        pre_val = (float*)take((size_t)n * 4);
+    }
+};
+
+struct RoundParams {
+    // index
+    const float* codes;
+    const long long* list_off;
+    const long long* ids;
+    int dpad;
+    long nlist;
+    int metric;
+    // queries
+    const float* xq;      // n x dpad
+    const int* ckeys;     // n x nlist ranked centroid ids
+    const float* cdis;    // n x nlist ranked centroid distances
+    long n;
+    int K;
+    // round
+    const int* active;    // n_active -> query
+    int n_active;
+    int r0, w, S;
+    // plan
+    int* list_cnt;
+    int* list_pair_off;   // nlist + 1
+    int* list_tile_off;   // nlist + 1
+    int* list_cursor;
+    unsigned long long* pairs;
+    int* ctl;
+    // pool: slot = (a * w + p_rel) * S + seg, K entries each
+    float* cand_d;
+    unsigned* cand_off;
+    int* slot_cnt;
+    QState st;
+};
+
+void launch_plan(const RoundParams& rp, cudaStream_t s);
+void launch_scan(const RoundParams& rp, int num_sms, cudaStream_t s);
+
+}  // namespace auncel

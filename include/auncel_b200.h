@@ -1,0 +1,154 @@
+/*
+ * auncel_b200 -- C ABI of the B200-native error-bounded IVF-Flat query path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Conventions
+ * follow the reference's own C wrapper (/root/reference/Auncel/c_api): opaque handle, int
+ * status (0 ok; -1 unknown, -2 invalid argument / failed FAISS_THROW_IF_NOT-style check,
+ * -4 CUDA/runtime error: c_api/error_c.h:19-33), thread-local last error string
+ * (c_api/error_impl.cpp:17-28).  idx_t is 64-bit (Index.h:67); matrices are row-major and
+ * compact; the caller owns every buffer; missing results are label -1 with distance
+ * FLT_MAX (L2) / -FLT_MAX (IP) (Heap.h:295-322).
+ *
+ * Each entry point names the reference interface it replaces (paths relative to
+ * /root/reference/Auncel).  "host" entry points take host pointers and do their own
+ * host<->device copies; "_device" entry points take device pointers on the index's device
+ * and enqueue on the index's stream, returning after the results are complete.
+ */
+#ifndef AUNCEL_B200_H
+#define AUNCEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct AuncelIndex_H AuncelIndex;
+
+#define AUNCEL_METRIC_INNER_PRODUCT 0 /* Index.h:49 */
+#define AUNCEL_METRIC_L2 1            /* Index.h:50 */
+
+/* c_api/error_c.h: faiss_get_last_error */
+const char* auncel_get_last_error(void);
+
+/* error bits accumulated by a tuned search where the reference would have thrown or read
+ * out of bounds: 1 arcos domain (IVF_pro.cpp:180), 2 arcos x==1 (IVF_pro.cpp:182),
+ * 4 cosine_theorem precondition (IVF_pro.cpp:42). */
+
+/* IndexIVFFlat(quantizer, d, nlist, metric) with an IndexFlatL2/IP quantizer
+ * (IndexIVFFlat.h:26-28, c_api/IndexIVFFlat_c.h faiss_IndexIVFFlat_new_with_metric). */
+int auncel_index_new(AuncelIndex** out, int d, int64_t nlist, int metric, int device);
+/* c_api/Index_c.h faiss_Index_free */
+void auncel_index_free(AuncelIndex* idx);
+
+int auncel_index_d(const AuncelIndex* idx);
+int64_t auncel_index_nlist(const AuncelIndex* idx);
+int64_t auncel_index_ntotal(const AuncelIndex* idx);   /* Index::ntotal */
+int auncel_index_is_trained(const AuncelIndex* idx);   /* Index::is_trained */
+
+/* Import trained centroids (nlist x d, host) into the coarse quantizer -- the state
+ * Level1Quantizer::train_q1 leaves behind (IndexIVF.cpp:71-137).  compute_interdis != 0 also
+ * fills Auncel's pairwise centroid table interdis_cem (:97-117; what index->set_tune_mode()
+ * before train() enables, eval/bound.cpp:261-263). */
+int auncel_index_set_centroids(AuncelIndex* idx, const float* centroids, int compute_interdis);
+int auncel_index_get_centroids(const AuncelIndex* idx, float* out);
+/* packed strict upper triangle, nlist*(nlist-1)/2 floats (IVF_pro.cpp:21-39) */
+int auncel_index_get_interdis(const AuncelIndex* idx, float* out);
+int auncel_index_set_interdis(AuncelIndex* idx, const float* in);
+
+/* Index::train (IndexIVF.cpp:995-1008): k-means on the device (Clustering.cpp:77-244
+ * semantics: niter iterations, seed 1234, at most 256 points per centroid, spherical for IP)
+ * followed by set_centroids.  tune != 0 <=> set_tune_mode() was called before train(). */
+int auncel_index_train(AuncelIndex* idx, int64_t n, const float* x, int niter, int tune);
+
+/* IndexIVFFlat::add_core (IndexIVFFlat.cpp:41-80).  ids == NULL: ntotal + i.  list_no ==
+ * NULL: quantizer->assign (k = 1 coarse search); otherwise precomputed_idx (< 0 skips). */
+int auncel_index_add(AuncelIndex* idx, int64_t n, const float* x, const int64_t* ids,
+                     const int64_t* list_no);
+int auncel_index_add_device(AuncelIndex* idx, int64_t n, const float* x_dev, const int64_t* ids,
+                            const int64_t* list_no);
+/* Index::assign (Index.cpp:42-47) */
+int auncel_index_assign(AuncelIndex* idx, int64_t n, const float* x, int64_t* list_no);
+/* Index::reset */
+int auncel_index_reset(AuncelIndex* idx);
+/* InvertedLists::list_size for every list (InvertedLists.h:43) */
+int auncel_index_list_sizes(const AuncelIndex* idx, int64_t* out);
+
+/* quantizer->search(n, x, nprobe, coarse_dis, idx) (IndexFlat.cpp:42-56): the nprobe best
+ * centroids per query, best first, with the reference's exact per-pair arithmetic
+ * (knn_L2sqr_sse / knn_inner_product_sse, utils.cpp:417-490). */
+int auncel_index_coarse_search(AuncelIndex* idx, int64_t n, const float* x, int64_t nprobe,
+                               float* coarse_dis, int64_t* keys);
+
+/* IndexIVF::search (IndexIVF.cpp:335-353): fixed nprobe, optional max_codes (0 = off). */
+int auncel_index_search(AuncelIndex* idx, int64_t n, const float* x, int64_t k, int64_t nprobe,
+                        int64_t max_codes, float* distances, int64_t* labels);
+int auncel_index_search_device(AuncelIndex* idx, int64_t n, const float* x_dev, int64_t k,
+                               int64_t nprobe, int64_t max_codes, float* distances_dev,
+                               int64_t* labels_dev);
+
+/* error_pro state the online check needs (IVF_pro.h:82-114): n_traces ascending (phi, U,
+ * sigma) tables (Trace, IVF_pro.h:44-62) concatenated with trace_off[n_traces+1], and the
+ * two hyper-parameters of hyperparameter.txt / error_pro::setparam (IVF_pro.cpp:240-256). */
+int auncel_index_set_error_model(AuncelIndex* idx, int n_traces, const int64_t* trace_off,
+                                 const float* phi, const float* U, const float* sigma,
+                                 float multipler, float std_m);
+int auncel_index_set_params(AuncelIndex* idx, float multipler, float std_m);
+int auncel_index_n_traces(const AuncelIndex* idx);
+int64_t auncel_index_trace_size(const AuncelIndex* idx, int t);
+int auncel_index_get_trace(const AuncelIndex* idx, int t, float* phi, float* U, float* sigma);
+
+/* Error_sys::sys_train (profile.cpp:88-171) + error_pro::train (IVF_pro.cpp:186-194):
+ * calibration search of n queries (training block, IndexIVF.cpp:640-673) against their exact
+ * ground-truth distances gt_D (n x max_topk), then Trace::SB.  Installs the resulting error
+ * model.  distances/labels (n x max_topk, may be NULL) receive the calibration search result. */
+int auncel_index_calibrate(AuncelIndex* idx, int64_t n, const float* x, int64_t max_topk,
+                           const float* gt_D, float* distances, int64_t* labels);
+
+/* Error_sys::search (profile.cpp:211-227) -> IndexIVF::search(n, x, k, D, I, offset) with
+ * tune = true, nprobe = nlist (IndexIVF.cpp:355-378, tune block :551-638).
+ *   max_topk     width of the result heap (GT depth);  query_topk = error_pro::query_topk
+ *   require_acc  n targets, 1 - error bound            (error_pro::require_acc[id])
+ *   gt_kth       n ground-truth distances at rank query_topk-1, or NULL (only `profile`)
+ *   my_nprobe    n, in/out: error_pro::my_nprobe[id] (0 = undecided on input)
+ *   t_recalls    n, in/out, or NULL: error_pro::t_recalls[id]
+ *   flags        bit 0 = error_pro::profile, bit 1 = error_pro::overhead_profile */
+int auncel_index_search_bounded(AuncelIndex* idx, int64_t n, const float* x, int64_t max_topk,
+                                int64_t query_topk, const float* require_acc,
+                                const float* gt_kth, uint64_t* my_nprobe, float* t_recalls,
+                                int flags, float* distances, int64_t* labels);
+int auncel_index_search_bounded_device(AuncelIndex* idx, int64_t n, const float* x_dev,
+                                       int64_t max_topk, int64_t query_topk,
+                                       const float* require_acc_dev, const float* gt_kth_dev,
+                                       uint64_t* my_nprobe_dev, float* t_recalls_dev, int flags,
+                                       float* distances_dev, int64_t* labels_dev);
+
+/* IndexIVFStats (IndexIVF.h:361-374) of the last search on this index + engine counters.
+ * out[0]=nq [1]=nlist visited [2]=ndis [3]=search ms (device) [4]=rounds [5]=scan tiles
+ * [6]=(query,list) pairs scanned [7]=error bits */
+int auncel_index_get_stats(const AuncelIndex* idx, double* out8);
+
+/* scratch budget for per-round candidate pools, bytes (default 1 GiB) */
+int auncel_index_set_pool_budget(AuncelIndex* idx, size_t bytes);
+
+/* merge_tables (IndexShards.cpp:44-105): k-way merge of nshard sorted (n x k) result tables
+ * (layout [shard][query][rank]); labels < 0 end a shard's row; translations may be NULL. */
+int auncel_merge_tables(int metric, int64_t n, int64_t k, int64_t nshard, const float* all_distances,
+                        const int64_t* all_labels, const int64_t* translations, float* distances,
+                        int64_t* labels);
+int auncel_merge_tables_device(int device, int metric, int64_t n, int64_t k, int64_t nshard,
+                               const float* all_distances_dev, const int64_t* all_labels_dev,
+                               const int64_t* translations_dev, float* distances_dev,
+                               int64_t* labels_dev, void* cuda_stream);
+
+/* IndexIVF::copy_subset_to (IndexIVF.cpp:1055-1118): append to `other` (same centroids) the
+ * entries selected by subset_type 1 (id % a1 == a2) or 2 (proportional in-list slice a1..a2
+ * of ntotal).  This is how an index is split across GPUs (gpu/GpuAutoTune.cpp:201-220). */
+int auncel_index_copy_subset_to(const AuncelIndex* idx, AuncelIndex* other, int subset_type,
+                                int64_t a1, int64_t a2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

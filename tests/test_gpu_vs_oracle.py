@@ -1,0 +1,188 @@
+"""GPU vs the CPU restatement on seeded inputs the fixtures do not cover: dimensions that
+are not a multiple of 4 or 32, tiny and empty lists, k larger than a list, ragged batches,
+precomputed assignment, add in several calls, shards merge."""
+import numpy as np
+import pytest
+
+import auncel_b200 as ab
+from auncel_b200 import synth
+from oracle import oracle as O
+from tests.util import assert_results_match
+
+pytestmark = pytest.mark.gpu
+
+
+def build_pair(metric, d, nlist, nb, seed=3, n_centers=20):
+    norm = metric == O.IP
+    xb = synth.clustered(seed, nb, d, n_centers, 0.3, normalize=norm)
+    cent = synth.clustered(seed + 50, nlist, d, n_centers, 0.3, normalize=norm)
+    orc = O.OracleIndex(d, nlist, metric)
+    orc.set_centroids(cent)
+    orc.add(xb)
+    ix = ab.IndexIVFFlat(d, nlist, metric)
+    ix.set_centroids(cent)
+    ix.add(xb)
+    return xb, cent, orc, ix
+
+
+@pytest.mark.parametrize("metric,d", [(O.L2, 7), (O.L2, 32), (O.L2, 100), (O.IP, 12), (O.IP, 200), (O.L2, 960)])
+def test_fixed_various_dims(metric, d):
+    nlist, nb = 48, 3000 if d < 500 else 1500
+    xb, cent, orc, ix = build_pair(metric, d, nlist, nb)
+    xq = synth.clustered(9, 37, d, 20, 0.3, normalize=metric == O.IP)
+    assert np.array_equal(ix.assign(xb), orc.assign(xb))
+    for nprobe, k in [(1, 1), (3, 10), (48, 100), (7, 128)]:
+        ix.nprobe = nprobe
+        D, I = ix.search(xq, k)
+        D2, I2 = orc.search_fixed(xq, k, nprobe)
+        assert np.array_equal(D, D2), (nprobe, k)
+        assert_results_match(D, I, D2, I2, what=f"d={d} nprobe={nprobe} k={k}")
+
+
+def test_empty_and_tiny_lists_and_padding():
+    d, nlist = 16, 64
+    xb = synth.clustered(4, 40, d, 5, 0.2)  # fewer vectors than lists: most lists empty
+    cent = synth.clustered(5, nlist, d, 5, 0.5)
+    orc = O.OracleIndex(d, nlist, O.L2)
+    orc.set_centroids(cent)
+    orc.add(xb)
+    ix = ab.IndexIVFFlat(d, nlist, O.L2)
+    ix.set_centroids(cent)
+    ix.add(xb)
+    xq = synth.clustered(6, 5, d, 5, 0.2)
+    for nprobe in (1, 8, 64):
+        ix.nprobe = nprobe
+        D, I = ix.search(xq, 50)
+        D2, I2 = orc.search_fixed(xq, 50, nprobe)
+        assert np.array_equal(D, D2) and np.array_equal(I, I2)
+    assert (I == -1).any() and D.max() == np.finfo(np.float32).max
+    D, I = ix.search(xq[:0], 5)
+    assert D.shape == (0, 5)
+
+
+def test_add_in_pieces_with_ids_and_precomputed():
+    d, nlist = 20, 32
+    xb = synth.clustered(7, 2000, d)
+    cent = synth.clustered(8, nlist, d)
+    orc = O.OracleIndex(d, nlist, O.L2)
+    orc.set_centroids(cent)
+    ix = ab.IndexIVFFlat(d, nlist, O.L2)
+    ix.set_centroids(cent)
+    ids = np.arange(2000, dtype=np.int64)[::-1] * 3 + 7
+    pre = orc.assign(xb)
+    pre[5::97] = -1  # skipped vectors (IndexIVFFlat.cpp:65-66)
+    for a, b in [(0, 700), (700, 701), (701, 2000)]:
+        ix.add_core(xb[a:b], ids[a:b], pre[a:b])
+        orc.add(xb[a:b], ids[a:b], pre[a:b])
+    assert ix.ntotal == 2000
+    xq = synth.clustered(10, 33, d)
+    ix.nprobe = 5
+    D, I = ix.search(xq, 10)
+    D2, I2 = orc.search_fixed(xq, 10, 5)
+    assert np.array_equal(D, D2) and np.array_equal(I, I2)
+
+
+def test_error_messages():
+    ix = ab.IndexIVFFlat(8, 16)
+    with pytest.raises(ab.FaissException):
+        ix.add(np.zeros((3, 8), np.float32))  # not trained (IndexIVFFlat.cpp:45)
+    ix.set_centroids(synth.clustered(1, 16, 8))
+    ix.add(synth.clustered(2, 100, 8))
+    with pytest.raises(ab.FaissException):
+        ix.search(np.zeros((1, 8), np.float32), 1000)
+    with pytest.raises(ab.FaissException):
+        ix.search_bounded(np.zeros((1, 8), np.float32), 10, 5, np.ones(1, np.float32))  # no error model
+    with pytest.raises(ab.FaissException):
+        ab.Error_sys(ix, 15, 10)
+
+
+def test_bounded_vs_oracle_small_nlist():
+    """nlist = 64 (8 stages max, 4 traces): the whole tune path incl. calibration."""
+    for metric, d in [(O.L2, 12), (O.IP, 16)]:
+        nlist, nb, k, qk = 64, 20000, 16, 4
+        xb, cent, orc, ix = build_pair(metric, d, nlist, nb, n_centers=40)
+        xq = synth.clustered(21, 300, d, 40, 0.3, normalize=metric == O.IP)
+        if metric == O.IP:
+            sizes = ix.list_sizes()
+            dis, keys = orc.coarse(xq, 1)
+            xq = xq[(sizes[keys[:, 0]] >= k) & (dis[:, 0] <= 1.0)]
+        xq = xq[:len(xq) // 10 * 10]
+        n = len(xq)
+        ts = n // 2 // 10 * 10
+        gD, gI = orc.search_fixed(xq, k, nlist)
+        orc.calibrate(xq[:ts], gD[:ts])
+        es = ab.Error_sys(ix, n, k)
+        es.set_gt(gD, gI)
+        es.sys_train(ts, xq)
+        for a, b in zip(ix.traces(), orc.traces):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+        for mult, stdm, eb in [(1.0, 1.0, 0.1), (3.0, 0.5, 0.3)]:
+            acc = np.full(n, 1 - eb, np.float32)
+            orc.multipler, orc.std_m = mult, stdm
+            D2, I2, np2, tr2 = orc.search_bounded(xq[ts:], k, qk, acc, gt_D=gD, offset=ts)
+            assert orc.last_err == 0
+            ix.set_params(mult, stdm)
+            D, I, np1 = ix.search_bounded(xq[ts:], k, qk, acc[ts:])
+            assert np.array_equal(np1, np2[ts:])
+            assert np.array_equal(D, D2)
+            assert_results_match(D, I, D2, I2, what="bounded small")
+            assert ix.stats()["ndis"] == orc.last_stats["ndis"]
+            assert ix.stats()["nlist"] == orc.last_stats["nlist"]
+
+
+def test_merge_tables_and_shards():
+    d, nlist, nb, k = 16, 32, 4000, 10
+    xb, cent, orc, ix = build_pair(O.L2, d, nlist, nb)
+    xq = synth.clustered(31, 50, d)
+    subs = []
+    for s in range(3):
+        sub = ab.IndexIVFFlat(d, nlist, O.L2)
+        sub.set_centroids(cent, compute_interdis=False)
+        ix.copy_subset_to(sub, 1, 3, s)  # id % 3 == s
+        sub.nprobe = 4
+        subs.append(sub)
+    assert sum(s.ntotal for s in subs) == nb
+    allD = np.stack([s.search(xq, k)[0] for s in subs])
+    allI = np.stack([s.search(xq, k)[1] for s in subs])
+    D, I = ab.merge_tables(O.L2, allD, allI)
+    D2, I2 = O.merge_tables(O.L2, allD, allI)
+    assert np.array_equal(D, D2) and np.array_equal(I, I2)
+    ix.nprobe = 4
+    Df, If = ix.search(xq, k)
+    assert np.array_equal(D, Df)  # tests/test_merge.cpp invariant: shards == single index
+    # type 2 (proportional slices) also partitions the index
+    subs2 = []
+    for s in range(2):
+        sub = ab.IndexIVFFlat(d, nlist, O.L2)
+        sub.set_centroids(cent, compute_interdis=False)
+        ix.copy_subset_to(sub, 2, s * nb // 2, (s + 1) * nb // 2)
+        sub.nprobe = 4
+        subs2.append(sub)
+    assert sum(s.ntotal for s in subs2) == nb
+    allD = np.stack([s.search(xq, k)[0] for s in subs2])
+    allI = np.stack([s.search(xq, k)[1] for s in subs2])
+    D, I = ab.merge_tables(O.L2, allD, allI)
+    assert np.array_equal(D, Df)
+    # rows with missing results: -1 labels end a row (IndexShards.cpp:62-66)
+    allI[1, :, 3:] = -1
+    D, I = ab.merge_tables(O.L2, allD, allI)
+    D2, I2 = O.merge_tables(O.L2, allD, allI)
+    assert np.array_equal(D, D2) and np.array_equal(I, I2)
+
+
+def test_train_kmeans_runs_and_searches():
+    d, nlist = 16, 64
+    xb = synth.clustered(41, 20000, d, 30)
+    ix = ab.IndexIVFFlat(d, nlist)
+    ix.set_tune_mode()
+    ix.train(xb, niter=5)
+    ix.set_tune_off()
+    assert ix.is_trained
+    ix.add(xb)
+    cent = ix.centroids()
+    orc = O.OracleIndex(d, nlist, O.L2)
+    orc.set_centroids(cent)
+    assert np.array_equal(orc.interdis, ix.interdis_cem())
+    sizes = ix.list_sizes()
+    assert sizes.sum() == 20000 and (sizes > 0).mean() > 0.9
