@@ -552,6 +552,10 @@ int auncel_index_search_bounded(AuncelIndex* idx, int64_t n, const float* x, int
 
 int auncel_index_get_stats(const AuncelIndex* idx, double* out8) {
     const SearchStats& st = idx->ix.stats;
+    out8[8] = st.scan_ms;
+    out8[9] = (double)st.launches;
+    out8[10] = (double)st.scan_launches;
+    out8[11] = st.coarse_ms;
     out8[0] = (double)st.nq;
     out8[1] = (double)st.nlist;
     out8[2] = (double)st.ndis;

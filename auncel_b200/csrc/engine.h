@@ -68,7 +68,8 @@ constexpr int SCAN_THREADS = 256;
 struct SearchStats {  // IndexIVFStats, IndexIVF.h:361-374
     uint64_t nq = 0, nlist = 0, ndis = 0, nheap_updates = 0;
     double quantization_ms = 0, search_ms = 0;
-    uint64_t rounds = 0, scan_tiles = 0, scan_pairs = 0;
+    uint64_t rounds = 0, scan_tiles = 0, scan_pairs = 0, launches = 0, scan_launches = 0;
+    double coarse_ms = 0;
     double scan_ms = 0;      // device time of the scan kernels of the last search
     uint64_t err_bits = 0;   // ERR_* bits raised by the last search
 };
@@ -140,7 +141,8 @@ struct IvfIndex {
 
     size_t pool_budget_bytes = (size_t)1 << 30;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    std::vector<cudaEvent_t> scan_ev;  // pairs of events around every scan launch
     SearchStats stats;
     int num_sms = 148;
 

@@ -17,6 +17,7 @@ IvfIndex::IvfIndex(int d_, long nlist_, int metric_, int device_)
     CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaEventCreate(&ev0));
     CUDA_CHECK(cudaEventCreate(&ev1));
+    CUDA_CHECK(cudaEventCreate(&ev2));
     h_list_off.assign(nlist + 1, 0);
     list_off.ensure(nlist + 1);
     CUDA_CHECK(cudaMemset(list_off.p, 0, (nlist + 1) * sizeof(long long)));
@@ -36,6 +37,8 @@ IvfIndex::~IvfIndex() {
     if (stream) cudaStreamDestroy(stream);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (ev2) cudaEventDestroy(ev2);
+    for (auto e : scan_ev) cudaEventDestroy(e);
 }
 
 void IvfIndex::set_centroids(const float* c, bool compute_interdis) {
@@ -349,7 +352,10 @@ void IvfIndex::search(const QueryBatch& qb) {
         xs = q_x.p;
     }
     coarse_rank(n, xs);
+    CUDA_CHECK(cudaEventRecord(ev2, stream));
     CUDA_CHECK(cudaMemsetAsync(ctl.p, 0, (CTL_SIZE + 8) * sizeof(int), stream));
+    uint64_t launches = 2 * ((n + 65535L * 64 - 1) / (65535L * 64)) + (dpad != d ? 1 : 0) + 2 /*init, finalize*/ +
+                        (qb.mode != 0 ? 1 : 0);
 
     // ---- per-query state
     state.ensure(QState::bytes(n, K));
@@ -431,9 +437,19 @@ void IvfIndex::search(const QueryBatch& qb) {
         rp.slot_cnt = slot_cnt.ensure(slots);
         rp.pairs = pairs.ensure((size_t)n_active * w);
 
+        if (scan_ev.size() < 2 * (stats.rounds + 1)) {
+            cudaEvent_t a, b;
+            CUDA_CHECK(cudaEventCreate(&a));
+            CUDA_CHECK(cudaEventCreate(&b));
+            scan_ev.push_back(a);
+            scan_ev.push_back(b);
+        }
         launch_plan(rp, stream);
+        CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds], stream));
         launch_scan(rp, num_sms, stream);
+        CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds + 1], stream));
         launch_merge_check(rp, tp, stream);
+        launches += 6;  // plan x3, scan, merge_check, compact_active
         launch_compact_active(rp, r0 + (int)w, act_nxt, h_ctl.p, stream);
         CUDA_CHECK(cudaStreamSynchronize(stream));
         n_active = h_ctl.p[CTL_N_ACTIVE];
@@ -460,7 +476,17 @@ void IvfIndex::search(const QueryBatch& qb) {
     stats.nlist = h_st[0];
     stats.ndis = h_st[1];
     stats.search_ms = ms;
+    for (uint64_t r = 0; r < stats.rounds; r++) {
+        float t = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&t, scan_ev[2 * r], scan_ev[2 * r + 1]));
+        scan_ms_total += t;
+    }
     stats.scan_ms = scan_ms_total;
+    stats.scan_launches = stats.rounds;
+    stats.launches = launches;
+    float cms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&cms, ev0, ev2));
+    stats.coarse_ms = cms;
     stats.err_bits = (uint64_t)h_ctl.p[CTL_ERR];
 }
 

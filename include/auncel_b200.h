@@ -126,8 +126,9 @@ int auncel_index_search_bounded_device(AuncelIndex* idx, int64_t n, const float*
 
 /* IndexIVFStats (IndexIVF.h:361-374) of the last search on this index + engine counters.
  * out[0]=nq [1]=nlist visited [2]=ndis [3]=search ms (device) [4]=rounds [5]=scan tiles
- * [6]=(query,list) pairs scanned [7]=error bits */
-int auncel_index_get_stats(const AuncelIndex* idx, double* out8);
+ * [6]=(query,list) pairs scanned [7]=error bits [8]=scan-kernel ms (CUDA events around every
+ * scan launch) [9]=kernel launches [10]=scan-kernel launches [11]=coarse ms.  out: 12 doubles */
+int auncel_index_get_stats(const AuncelIndex* idx, double* out12);
 
 /* scratch budget for per-round candidate pools, bytes (default 1 GiB) */
 int auncel_index_set_pool_budget(AuncelIndex* idx, size_t bytes);
