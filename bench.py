@@ -331,7 +331,9 @@ def cpu_baseline(a, S, np_gpu, D_gpu):
             "sample": f"first {nsample} test queries, one batched Error_sys::search on {cores} host threads "
                       f"(unmodified reference, exact-difference coarse path, OpenBLAS unused), {dt:.2f} s",
             "parity_on_sample": {"my_nprobe_equal": bool(np.array_equal(mynp.astype(np.int64), np_gpu[:nsample])),
-                                 "distances_bit_equal": bool(np.array_equal(D, D_gpu[:nsample]))}}
+                                 "distances_bit_equal": bool(np.array_equal(D, D_gpu[:nsample])),
+                                 "my_nprobe_mismatches": [[int(i), int(mynp[i]), int(np_gpu[i])] for i in
+                                                          np.flatnonzero(mynp.astype(np.int64) != np_gpu[:nsample])[:8]]}}
 
 
 def run_reference(a):
