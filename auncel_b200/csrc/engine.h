@@ -110,6 +110,7 @@ struct IvfIndex {
     DevBuf<long long> ids;     // ntotal
     DevBuf<long long> list_off;  // nlist + 1 (in vectors)
     std::vector<long long> h_list_off;
+    alignas(64) unsigned char codes_tmap[128];  // CUtensorMap over `codes` (rebuilt by add)
 
     // error model (device copies + host mirror)
     std::vector<float> h_arcos;

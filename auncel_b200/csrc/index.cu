@@ -234,6 +234,7 @@ void IvfIndex::add_device(long n, const float* x_dev, const long long* ids_host,
     std::swap(ids.p, nids.p);
     std::swap(ids.cap, nids.cap);
     h_list_off = new_off;
+    make_codes_tensor_map(codes_tmap, codes.p, new_total, dpad);
     ntotal += n;  // the reference counts skipped (-1) vectors too, IndexIVFFlat.cpp:79
 }
 
@@ -404,7 +405,7 @@ void IvfIndex::search(const QueryBatch& qb) {
     launch_init_state(rp, tp, qb.mode == 1 ? qb.my_nprobe : nullptr, active.p, stream);
 
     // ---- rounds
-    int n_active = (int)n;
+    int n_active = h_list_off[nlist] > 0 ? (int)n : 0;  // an empty index has nothing to scan
     int r0 = 0;
     int* act_cur = active.p;
     int* act_nxt = active2.p;
@@ -418,7 +419,13 @@ void IvfIndex::search(const QueryBatch& qb) {
         long w_cap = (long)(pool_entries / ((size_t)n_active * K));
         w_cap = std::max(1L, std::min<long>(w_cap, 1024));
         long w = max_stage - r0;
-        if (qb.mode == 1 && !qb.overhead_profile) w = std::min<long>(w, std::max(1, r0));
+        if (qb.mode == 1 && !qb.overhead_profile) {
+            w = std::min<long>(w, std::max(1, r0));
+        } else if ((long)n_active * max_stage >= 4096 && max_stage > 8) {
+            // plain / calibration search: a few narrow rounds first, so that the bulk of the
+            // lists is scanned against a tight threshold (cheap selection)
+            w = std::min<long>(w, std::max(2, 2 * r0));
+        }
         w = std::min(w, w_cap);
         // segments: split lists when there are too few (list, query-tile) units to fill the GPU
         long est_tiles = std::min<long>((long)n_active * w, nlist) + (long)n_active * w / SCAN_QT;
@@ -446,7 +453,7 @@ void IvfIndex::search(const QueryBatch& qb) {
         }
         launch_plan(rp, stream);
         CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds], stream));
-        launch_scan(rp, num_sms, stream);
+        launch_scan(rp, codes_tmap, num_sms, stream);
         CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds + 1], stream));
         launch_merge_check(rp, tp, stream);
         launches += 6;  // plan x3, scan, merge_check, compact_active

@@ -8,8 +8,19 @@
 // (query, list segment), the K best candidates that beat the query's threshold tau (the K-th
 // best distance it already holds): exactly the candidates the reference's strict
 // `C::cmp(simi[0], dis)` test could ever accept (IndexIVFFlat.cpp:129).
-#include "scan.cuh"
+//
+// Kernel structure (sm_100a): persistent CTAs, warp specialised.
+//   warp 8      producer: claims tiles (atomic counter), decodes them, and per k-chunk issues
+//               one TMA 2D tile load (128 list rows x 32 floats, SWIZZLE_128B) plus one
+//               cp.async.bulk row per query of the tile, all completing on the stage's mbarrier
+//   warps 0..7  consumers: wait on the stage's `full` mbarrier, accumulate a 4-query x
+//               4-vector register tile each (lanes <-> vectors, warps <-> queries), release the
+//               stage on its `empty` mbarrier, and run selection privately -- no CTA barrier
+//               in the steady state, so a warp that is sorting never stalls the others.
+#include <cuda.h>
+
 #include "exact.cuh"
+#include "scan.cuh"
 
 namespace auncel {
 
@@ -95,19 +106,68 @@ void launch_plan(const RoundParams& rp, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------- scan
+constexpr int NCONS = 8;                          // consumer warps
+constexpr int THREADS = (NCONS + 1) * 32;         // + 1 producer warp
 constexpr int STAGES = 4;
-constexpr int LD = SCAN_DK + 4;                 // padded smem row, floats
-constexpr int CAP = 256;                        // candidate buffer per query (>= MAX_K + 32)
-constexpr int STAGE_FLOATS = (SCAN_VT + SCAN_QT) * LD;
-constexpr size_t SCAN_SMEM = (size_t)STAGES * STAGE_FLOATS * 4 + (size_t)SCAN_QT * CAP * 8 + 1024;
+constexpr int QLD = SCAN_DK + 4;                  // padded query row, floats
+constexpr int VT_BYTES = SCAN_VT * SCAN_DK * 4;   // 16384: 128 rows x 128 B, 128B-swizzled by TMA
+constexpr int QT_BYTES = SCAN_QT * QLD * 4;       // 4608
+constexpr int HDR_BYTES = 512;
+constexpr int STAGE_BYTES = VT_BYTES + QT_BYTES + HDR_BYTES;  // 21504 = 21 * 1024
+constexpr int CAP = 256;                          // candidate buffer per query (>= MAX_K + 32)
+constexpr size_t SCAN_SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)SCAN_QT * CAP * 8;
+static_assert(STAGE_BYTES % 1024 == 0, "stages must keep the 1024 B alignment SWIZZLE_128B needs");
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+struct StageHdr {
+    int flags;       // 1 = end of work
+    int first;       // first stage of a tile
+    int last_chunk;  // last k-chunk of a vector block -> epilogue
+    int last_iter;   // last stage of the tile -> write results
+    int blk;         // vector block inside the segment
+    int nk;          // valid floats in this k-chunk (multiple of 4, <= 32)
+    int Qt;          // queries in the tile
+    int v_begin;     // first list offset of the segment
+    int nvec;        // vectors in the segment
+    int pad[7];
+    int slot[SCAN_QT];
+    float tau[SCAN_QT];
+};
+static_assert(sizeof(StageHdr) <= HDR_BYTES, "header too large");
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok = 0;
+    const unsigned addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 // warp-cooperative bitonic sort of N (power of two) 64-bit keys in shared memory
 template <int N>
@@ -132,6 +192,21 @@ __device__ __forceinline__ void warp_sort_smem(unsigned long long* key, int lane
     }
 }
 
+// one key per lane, ascending across lanes
+__device__ __forceinline__ unsigned long long warp_sort_reg(unsigned long long key, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j);
+            bool up = ((lane & k) == 0), lower = ((lane & j) == 0);
+            unsigned long long mn = key < other ? key : other, mx = key < other ? other : key;
+            key = (lower == up) ? mn : mx;
+        }
+    }
+    return key;
+}
+
 template <int METRIC>
 __device__ __forceinline__ unsigned long long make_key(float d, unsigned off) {
     uint32_t o = f2ord(d);
@@ -148,199 +223,284 @@ __device__ __forceinline__ float key_dist(unsigned long long key) {
 // sort the buffer, keep the K best, tighten tau when K are held
 template <int METRIC>
 __device__ __forceinline__ void compact(unsigned long long* buf, int& cnt, float& tau, int K, int lane) {
-    for (int i = cnt + lane; i < CAP; i += 32) buf[i] = ~0ull;
-    __syncwarp();
-    warp_sort_smem<CAP>(buf, lane);
+    if (cnt <= 64) {
+        for (int i = cnt + lane; i < 64; i += 32) buf[i] = ~0ull;
+        __syncwarp();
+        warp_sort_smem<64>(buf, lane);
+    } else if (cnt <= 128) {
+        for (int i = cnt + lane; i < 128; i += 32) buf[i] = ~0ull;
+        __syncwarp();
+        warp_sort_smem<128>(buf, lane);
+    } else {
+        for (int i = cnt + lane; i < CAP; i += 32) buf[i] = ~0ull;
+        __syncwarp();
+        warp_sort_smem<CAP>(buf, lane);
+    }
     if (cnt > K) cnt = K;
     if (cnt == K) tau = key_dist<METRIC>(buf[K - 1]);
     __syncwarp();
 }
 
 template <int METRIC>
-__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(RoundParams rp) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* stage_base = reinterpret_cast<float*>(smem_raw);
-    unsigned long long* cand = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)STAGES * STAGE_FLOATS * 4);
-    __shared__ int s_tile;
-    __shared__ int s_q[SCAN_QT];        // query index of each tile row (-1: none)
-    __shared__ int s_slot[SCAN_QT];     // pool slot of each tile row
-    __shared__ float s_tau[SCAN_QT];
+__global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES];
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    unsigned long long* cand = reinterpret_cast<unsigned long long*>(smem + (size_t)STAGES * STAGE_BYTES);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = rp.K, dpad = rp.dpad;
-    const int nchunk = (dpad + SCAN_DK - 1) / SCAN_DK;
-    const int total_tiles = rp.ctl[CTL_TOTAL_TILES];
 
-    while (true) {
-        __syncthreads();
-        if (tid == 0) s_tile = atomicAdd(&rp.ctl[CTL_TILE_COUNTER], 1);
-        __syncthreads();
-        const int T = s_tile;
-        if (T >= total_tiles) break;
-
-        // ---- decode tile -> (list, query tile, segment)
-        int lo = 0, hi = (int)rp.nlist;  // last l with list_tile_off[l] <= T
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (rp.list_tile_off[mid] <= T) lo = mid; else hi = mid;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NCONS);
         }
-        const int l = lo;
-        const int cnt_l = rp.list_pair_off[l + 1] - rp.list_pair_off[l];
-        const int nqt = (cnt_l + SCAN_QT - 1) / SCAN_QT;
-        const int tl = T - rp.list_tile_off[l];
-        const int seg = tl / nqt, qt = tl - seg * nqt;
-        const long long L0 = rp.list_off[l];
-        const int L = (int)(rp.list_off[l + 1] - L0);
-        int seg_len = (L + rp.S - 1) / rp.S;
-        seg_len = (seg_len + 31) / 32 * 32;
-        const int v_begin = seg * seg_len;
-        const int v_end = min(L, v_begin + seg_len);
-        const int Qt = min(SCAN_QT, cnt_l - qt * SCAN_QT);
-        if (v_begin >= v_end) continue;  // empty segment: slot_cnt stays 0
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
-        if (tid < SCAN_QT) {
+    if (warp == NCONS) {
+        // =========================== producer ===========================
+        const int nchunk = (dpad + SCAN_DK - 1) / SCAN_DK;
+        const int total_tiles = rp.ctl[CTL_TOTAL_TILES];
+        unsigned it = 0;
+        while (true) {
+            int T = 0;
+            if (lane == 0) T = atomicAdd(&rp.ctl[CTL_TILE_COUNTER], 1);
+            T = __shfl_sync(0xffffffffu, T, 0);
+            if (T >= total_tiles) break;
+            // decode tile -> (list, segment, query tile); segment-major so that neighbouring
+            // tiles share list rows in L2
+            int lo = 0, hi = (int)rp.nlist;
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (rp.list_tile_off[mid] <= T) lo = mid; else hi = mid;
+            }
+            const int l = lo;
+            const int cnt_l = rp.list_pair_off[l + 1] - rp.list_pair_off[l];
+            const int nqt = (cnt_l + SCAN_QT - 1) / SCAN_QT;
+            const int tl = T - rp.list_tile_off[l];
+            const int seg = tl / nqt, qt = tl - seg * nqt;
+            const long long L0 = rp.list_off[l];
+            const int L = (int)(rp.list_off[l + 1] - L0);
+            int seg_len = (L + rp.S - 1) / rp.S;
+            seg_len = (seg_len + 31) / 32 * 32;
+            const int v_begin = seg * seg_len;
+            const int v_end = min(L, v_begin + seg_len);
+            if (v_begin >= v_end) continue;  // empty segment: slot_cnt stays 0
+            const int Qt = min(SCAN_QT, cnt_l - qt * SCAN_QT);
             int q = -1, slot = 0;
             float tau = 0.f;
-            if (tid < Qt) {
-                unsigned long long pr = rp.pairs[rp.list_pair_off[l] + qt * SCAN_QT + tid];
+            if (lane < Qt) {
+                unsigned long long pr = rp.pairs[rp.list_pair_off[l] + qt * SCAN_QT + lane];
                 int a = (int)(pr >> 32), p_rel = (int)(pr & 0xffffffffu);
                 q = rp.active[a];
                 slot = (a * rp.w + p_rel) * rp.S + seg;
                 tau = rp.st.tau[q];
             }
-            s_q[tid] = q;
-            s_slot[tid] = slot;
-            s_tau[tid] = tau;
-        }
-        __syncthreads();
-
-        const int nblk = (v_end - v_begin + SCAN_VT - 1) / SCAN_VT;
-        const int total_it = nblk * nchunk;
-        const float* lbase = rp.codes + (L0 + v_begin) * (long long)dpad;
-        const int nvec = v_end - v_begin;
-
-        auto issue = [&](int it) {
-            if (it < total_it) {
-                int blk = it / nchunk, c = it - blk * nchunk;
-                float* sv = stage_base + (size_t)(it % STAGES) * STAGE_FLOATS;
-                float* sq = sv + SCAN_VT * LD;
-                int k0 = c * SCAN_DK;
-                // vectors: 128 rows x 8 x 16B
-#pragma unroll
-                for (int t = 0; t < (SCAN_VT * 8) / SCAN_THREADS; t++) {
-                    int idx = tid + t * SCAN_THREADS;
-                    int r = idx >> 3, cc = (idx & 7) * 4;
-                    int v = blk * SCAN_VT + r;
-                    bool ok = v < nvec && k0 + cc < dpad;
-                    const float* src = ok ? lbase + (long long)v * dpad + k0 + cc : rp.codes;
-                    cp_async16(sv + r * LD + cc, src, ok ? 16 : 0);
-                }
-                // queries: 32 rows x 8 x 16B
-                {
-                    int r = tid >> 3, cc = (tid & 7) * 4;
-                    int q = s_q[r];
-                    bool ok = q >= 0 && k0 + cc < dpad;
-                    const float* src = ok ? rp.xq + (long long)q * dpad + k0 + cc : rp.xq;
-                    cp_async16(sq + r * LD + cc, src, ok ? 16 : 0);
+            const float* qrow = rp.xq + (long long)(q < 0 ? 0 : q) * dpad;
+            const int nvec = v_end - v_begin;
+            const int nblk = (nvec + SCAN_VT - 1) / SCAN_VT;
+            const long long row0 = L0 + v_begin;
+            for (int blk = 0; blk < nblk; blk++) {
+                for (int c = 0; c < nchunk; c++, it++) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                    unsigned char* st = smem + (size_t)s * STAGE_BYTES;
+                    StageHdr* h = reinterpret_cast<StageHdr*>(st + VT_BYTES + QT_BYTES);
+                    const int k0 = c * SCAN_DK;
+                    const int nk = min(SCAN_DK, dpad - k0);
+                    if (lane == 0) {
+                        h->flags = 0;
+                        h->first = (blk == 0 && c == 0);
+                        h->last_chunk = (c == nchunk - 1);
+                        h->last_iter = (blk == nblk - 1 && c == nchunk - 1);
+                        h->blk = blk;
+                        h->nk = nk;
+                        h->Qt = Qt;
+                        h->v_begin = v_begin;
+                        h->nvec = nvec;
+                    }
+                    h->slot[lane] = slot;
+                    h->tau[lane] = tau;
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_expect_tx(&full_bar[s], (unsigned)(VT_BYTES + Qt * nk * 4));
+                        tma_load_2d(st, &tmap, k0, (int)(row0 + (long long)blk * SCAN_VT), &full_bar[s]);
+                    }
+                    if (lane < Qt) bulk_load(st + VT_BYTES + lane * QLD * 4, qrow + k0, (unsigned)(nk * 4), &full_bar[s]);
                 }
             }
-            cp_async_commit();
-        };
+        }
+        // end marker
+        {
+            const int s = it % STAGES;
+            mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+            StageHdr* h = reinterpret_cast<StageHdr*>(smem + (size_t)s * STAGE_BYTES + VT_BYTES + QT_BYTES);
+            if (lane == 0) {
+                h->flags = 1;
+                mbar_arrive(&full_bar[s]);
+            }
+        }
+        return;
+    }
 
-        // per-warp selection state for its 4 queries
-        const bool warp_has_q = warp * 4 < Qt;
-        int cnt[4] = {0, 0, 0, 0};
-        float tau[4];
+    // =========================== consumers ===========================
+    int cnt[4] = {0, 0, 0, 0};
+    float tau[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[4][4][4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) tau[i] = s_tau[warp * 4 + i];
-        float acc[4][4][4];
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++)
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-#pragma unroll
-                for (int x = 0; x < 4; x++) acc[i][j][x] = 0.f;
+            for (int x = 0; x < 4; x++) acc[i][j][x] = 0.f;
+    const int xr = lane & 7;  // SWIZZLE_128B: 16-byte chunk index is XORed with (row & 7)
 
+    for (unsigned it = 0;; it++) {
+        const int s = it % STAGES;
+        mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        const unsigned char* st = smem + (size_t)s * STAGE_BYTES;
+        const StageHdr* h = reinterpret_cast<const StageHdr*>(st + VT_BYTES + QT_BYTES);
+        if (h->flags) break;
+        const int Qt = h->Qt;
+        const bool has_q = warp * 4 < Qt;
+        const int last_chunk = h->last_chunk, last_iter = h->last_iter;
+        const int blk = h->blk, nvec = h->nvec, v_begin = h->v_begin, nk = h->nk;
+        int slot[4];
+        if (h->first) {
 #pragma unroll
-        for (int s = 0; s < STAGES - 1; s++) issue(s);
+            for (int i = 0; i < 4; i++) {
+                tau[i] = h->tau[warp * 4 + i];
+                cnt[i] = 0;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) slot[i] = h->slot[warp * 4 + i];
 
-        for (int it = 0; it < total_it; it++) {
-            cp_async_wait<STAGES - 2>();
-            __syncthreads();
-            issue(it + STAGES - 1);
-            const int blk = it / nchunk, c = it - blk * nchunk;
-            if (warp_has_q) {
-                const float* sv = stage_base + (size_t)(it % STAGES) * STAGE_FLOATS;
-                const float* sq = sv + SCAN_VT * LD + warp * 4 * LD;
+        if (has_q) {
+            const unsigned char* sv = st + lane * 128;
+            const float* sq = reinterpret_cast<const float*>(st + VT_BYTES) + warp * 4 * QLD;
+            if (nk == SCAN_DK) {
 #pragma unroll
-                for (int kk = 0; kk < SCAN_DK; kk += 4) {
+                for (int kc = 0; kc < SCAN_DK / 4; kc++) {
                     float4 a[4], b[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4*>(sq + i * LD + kk);
+                    for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4*>(sq + i * QLD + kc * 4);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) b[j] = *reinterpret_cast<const float4*>(sv + (lane + 32 * j) * LD + kk);
+                    for (int j = 0; j < 4; j++)
+                        b[j] = *reinterpret_cast<const float4*>(sv + j * (32 * 128) + ((kc ^ xr) << 4));
 #pragma unroll
                     for (int i = 0; i < 4; i++)
 #pragma unroll
                         for (int j = 0; j < 4; j++) exact_step<METRIC>(acc[i][j], a[i], b[j]);
                 }
-                if (c == nchunk - 1) {
-                    // ---- epilogue: filter against tau, append, compact when needed
+            } else {
+                for (int kc = 0; kc < nk / 4; kc++) {
+                    float4 a[4], b[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        unsigned long long* buf = cand + (size_t)(warp * 4 + i) * CAP;
-                        const bool qok = warp * 4 + i < Qt;
+                    for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4*>(sq + i * QLD + kc * 4);
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            float dist = exact_finish(acc[i][j]);
-                            acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
-                            int v = blk * SCAN_VT + lane + 32 * j;
-                            bool pass = qok && v < nvec &&
-                                        (METRIC == METRIC_L2 ? dist < tau[i] : dist > tau[i]);
-                            unsigned m = __ballot_sync(0xffffffffu, pass);
-                            if (m) {
-                                if (cnt[i] + 32 > CAP) compact<METRIC>(buf, cnt[i], tau[i], K, lane);
-                                // tau may have tightened: re-test
-                                pass = pass && (METRIC == METRIC_L2 ? dist < tau[i] : dist > tau[i]);
-                                m = __ballot_sync(0xffffffffu, pass);
-                                if (pass) {
-                                    int pos = cnt[i] + __popc(m & ((1u << lane) - 1));
-                                    buf[pos] = make_key<METRIC>(dist, (unsigned)(v_begin + v));
-                                }
-                                cnt[i] += __popc(m);
-                                __syncwarp();
-                            }
+                    for (int j = 0; j < 4; j++)
+                        b[j] = *reinterpret_cast<const float4*>(sv + j * (32 * 128) + ((kc ^ xr) << 4));
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) exact_step<METRIC>(acc[i][j], a[i], b[j]);
+                }
+            }
+        }
+        // the stage's data and header are consumed: hand the slot back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+
+        if (has_q && last_chunk) {
+            // ---- epilogue: filter against tau, append, compact when the buffer fills
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                unsigned long long* buf = cand + (size_t)(warp * 4 + i) * CAP;
+                const bool qok = warp * 4 + i < Qt;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float dist = exact_finish(acc[i][j]);
+                    acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+                    int v = blk * SCAN_VT + lane + 32 * j;
+                    bool pass = qok && v < nvec && (METRIC == METRIC_L2 ? dist < tau[i] : dist > tau[i]);
+                    unsigned m = __ballot_sync(0xffffffffu, pass);
+                    if (m) {
+                        if (cnt[i] + 32 > CAP) {
+                            compact<METRIC>(buf, cnt[i], tau[i], K, lane);
+                            pass = pass && (METRIC == METRIC_L2 ? dist < tau[i] : dist > tau[i]);
+                            m = __ballot_sync(0xffffffffu, pass);
                         }
+                        if (pass) buf[cnt[i] + __popc(m & ((1u << lane) - 1))] = make_key<METRIC>(dist, (unsigned)(v_begin + v));
+                        cnt[i] += __popc(m);
+                        __syncwarp();
                     }
                 }
             }
         }
-        cp_async_wait<0>();
-
-        // ---- write the per-(query, segment) candidates: sorted, at most K
-        if (warp_has_q) {
+        if (has_q && last_iter) {
+            // ---- per-(query, segment) result: sorted, at most K candidates
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                if (warp * 4 + i >= Qt) continue;
-                unsigned long long* buf = cand + (size_t)(warp * 4 + i) * CAP;
-                compact<METRIC>(buf, cnt[i], tau[i], K, lane);
-                const long slot = s_slot[warp * 4 + i];
-                for (int t = lane; t < cnt[i]; t += 32) {
-                    unsigned long long key = buf[t];
-                    rp.cand_d[slot * K + t] = key_dist<METRIC>(key);
-                    rp.cand_off[slot * K + t] = (unsigned)(key & 0xffffffffu);
+                if (warp * 4 + i < Qt && cnt[i] > 0) {
+                    unsigned long long* buf = cand + (size_t)(warp * 4 + i) * CAP;
+                    const long sl = slot[i];
+                    if (cnt[i] <= 32) {
+                        unsigned long long key = lane < cnt[i] ? buf[lane] : ~0ull;
+                        key = warp_sort_reg(key, lane);
+                        const int c = min(cnt[i], K);
+                        if (lane < c) {
+                            rp.cand_d[sl * K + lane] = key_dist<METRIC>(key);
+                            rp.cand_off[sl * K + lane] = (unsigned)(key & 0xffffffffu);
+                        }
+                        if (lane == 0) rp.slot_cnt[sl] = c;
+                    } else {
+                        compact<METRIC>(buf, cnt[i], tau[i], K, lane);
+                        for (int t = lane; t < cnt[i]; t += 32) {
+                            unsigned long long key = buf[t];
+                            rp.cand_d[sl * K + t] = key_dist<METRIC>(key);
+                            rp.cand_off[sl * K + t] = (unsigned)(key & 0xffffffffu);
+                        }
+                        if (lane == 0) rp.slot_cnt[sl] = cnt[i];
+                    }
+                    __syncwarp();
                 }
-                if (lane == 0) rp.slot_cnt[slot] = cnt[i];
-                __syncwarp();
             }
         }
     }
 }
 
-void launch_scan(const RoundParams& rp, int num_sms, cudaStream_t s) {
+// -------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+void make_codes_tensor_map(void* out_map, const float* codes, long long nrows, int dpad) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        AUNCEL_CHECK(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled unavailable");
+        fn = (EncodeTiledFn)p;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)dpad, (cuuint64_t)std::max<long long>(nrows, 1)};
+    cuuint64_t gstride[1] = {(cuuint64_t)dpad * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)SCAN_DK, (cuuint32_t)SCAN_VT};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)codes, gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AUNCEL_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+}
+
+void launch_scan(const RoundParams& rp, const void* tmap, int num_sms, cudaStream_t s) {
     auto kern = rp.metric == METRIC_L2 ? scan_kernel<METRIC_L2> : scan_kernel<METRIC_IP>;
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
-    kern<<<num_sms, SCAN_THREADS, SCAN_SMEM, s>>>(rp);
+    kern<<<num_sms, THREADS, SCAN_SMEM, s>>>(rp, *reinterpret_cast<const CUtensorMap*>(tmap));
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -74,6 +74,8 @@ struct RoundParams {
 };
 
 void launch_plan(const RoundParams& rp, cudaStream_t s);
-void launch_scan(const RoundParams& rp, int num_sms, cudaStream_t s);
+void launch_scan(const RoundParams& rp, const void* tensor_map, int num_sms, cudaStream_t s);
+// CUtensorMap (128 B, 64 B aligned) over the list arena [nrows x dpad] f32, box 128 rows x 32 floats
+void make_codes_tensor_map(void* out_map, const float* codes, long long nrows, int dpad);
 
 }  // namespace auncel
