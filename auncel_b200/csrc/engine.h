@@ -133,6 +133,7 @@ struct IvfIndex {
     DevBuf<int> active, active2;
     DevBuf<int> list_cnt, list_pair_off, list_tile_off, list_cursor;
     DevBuf<unsigned long long> pairs;
+    DevBuf<float> q_sorted;
     DevBuf<int> ctl;           // small control block (counters)
     PinnedBuf<int> h_ctl;
     DevBuf<float> io_f;        // host-API staging

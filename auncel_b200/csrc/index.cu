@@ -416,7 +416,7 @@ void IvfIndex::search(const QueryBatch& qb) {
         // window: fixed/calibration scans as wide as the pool allows; the error-bounded search
         // doubles its window (1,1,2,4,...) so undecided queries never speculate far past their
         // stop stage (with multipler >= 2 every speculative list is needed anyway).
-        long w_cap = (long)(pool_entries / ((size_t)n_active * K));
+        long w_cap = (long)(pool_budget_bytes / ((size_t)n_active * ((size_t)K * 8 + (size_t)dpad * 4)));
         w_cap = std::max(1L, std::min<long>(w_cap, 1024));
         long w = max_stage - r0;
         if (qb.mode == 1 && !qb.overhead_profile) {
@@ -443,6 +443,9 @@ void IvfIndex::search(const QueryBatch& qb) {
         rp.cand_off = reinterpret_cast<unsigned*>(pool.p + slots * K * 4);
         rp.slot_cnt = slot_cnt.ensure(slots);
         rp.pairs = pairs.ensure((size_t)n_active * w);
+        rp.xq_sorted = q_sorted.ensure(((size_t)n_active * w + SCAN_QT) * dpad);
+        alignas(64) unsigned char qmap[128];
+        make_queries_tensor_map(qmap, rp.xq_sorted, (long long)n_active * w + SCAN_QT, dpad);
 
         if (scan_ev.size() < 2 * (stats.rounds + 1)) {
             cudaEvent_t a, b;
@@ -453,10 +456,10 @@ void IvfIndex::search(const QueryBatch& qb) {
         }
         launch_plan(rp, stream);
         CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds], stream));
-        launch_scan(rp, codes_tmap, num_sms, stream);
+        launch_scan(rp, codes_tmap, qmap, num_sms, stream);
         CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds + 1], stream));
         launch_merge_check(rp, tp, stream);
-        launches += 6;  // plan x3, scan, merge_check, compact_active
+        launches += 7;  // plan x3, gather, scan, merge_check, compact_active
         launch_compact_active(rp, r0 + (int)w, act_nxt, h_ctl.p, stream);
         CUDA_CHECK(cudaStreamSynchronize(stream));
         n_active = h_ctl.p[CTL_N_ACTIVE];

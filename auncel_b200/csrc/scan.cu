@@ -94,6 +94,18 @@ __global__ void plan_fill_kernel(RoundParams rp) {
     rp.pairs[pos] = ((unsigned long long)(unsigned)a << 32) | (unsigned)p_rel;
 }
 
+// queries of the round, gathered in pair order: the query tile of a scan tile is then one
+// contiguous 32-row box that a single TMA load can fetch
+__global__ void gather_queries_kernel(RoundParams rp) {
+    long pos = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (pos >= rp.ctl[CTL_TOTAL_PAIRS]) return;
+    int a = (int)(rp.pairs[pos] >> 32);
+    const float4* src = reinterpret_cast<const float4*>(rp.xq + (long long)rp.active[a] * rp.dpad);
+    float4* dst = reinterpret_cast<float4*>(rp.xq_sorted + pos * rp.dpad);
+    for (int c = lane; c < rp.dpad / 4; c += 32) dst[c] = src[c];
+}
+
 void launch_plan(const RoundParams& rp, cudaStream_t s) {
     long tot = (long)rp.n_active * rp.w;
     CUDA_CHECK(cudaMemsetAsync(rp.list_cnt, 0, rp.nlist * sizeof(int), s));
@@ -102,6 +114,7 @@ void launch_plan(const RoundParams& rp, cudaStream_t s) {
     plan_count_kernel<<<blocks, 256, 0, s>>>(rp);
     plan_offsets_kernel<<<1, 1024, 0, s>>>(rp);
     plan_fill_kernel<<<blocks, 256, 0, s>>>(rp);
+    gather_queries_kernel<<<(unsigned)((tot * 32 + 255) / 256), 256, 0, s>>>(rp);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -109,11 +122,11 @@ void launch_plan(const RoundParams& rp, cudaStream_t s) {
 constexpr int NCONS = 8;                          // consumer warps
 constexpr int THREADS = (NCONS + 1) * 32;         // + 1 producer warp
 constexpr int STAGES = 4;
-constexpr int QLD = SCAN_DK + 4;                  // padded query row, floats
+constexpr int QLD = SCAN_DK;                      // query row in smem, floats (dense TMA box)
 constexpr int VT_BYTES = SCAN_VT * SCAN_DK * 4;   // 16384: 128 rows x 128 B, 128B-swizzled by TMA
-constexpr int QT_BYTES = SCAN_QT * QLD * 4;       // 4608
+constexpr int QT_BYTES = SCAN_QT * QLD * 4;       // 4096
 constexpr int HDR_BYTES = 512;
-constexpr int STAGE_BYTES = VT_BYTES + QT_BYTES + HDR_BYTES;  // 21504 = 21 * 1024
+constexpr int STAGE_BYTES = VT_BYTES + QT_BYTES + HDR_BYTES + 512;  // 21504 = 21 * 1024
 constexpr int CAP = 256;                          // candidate buffer per query (>= MAX_K + 32)
 constexpr size_t SCAN_SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)SCAN_QT * CAP * 8;
 static_assert(STAGE_BYTES % 1024 == 0, "stages must keep the 1024 B alignment SWIZZLE_128B needs");
@@ -242,7 +255,7 @@ __device__ __forceinline__ void compact(unsigned long long* buf, int& cnt, float
 }
 
 template <int METRIC>
-__global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap qmap) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES];
     unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -290,16 +303,15 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
             const int v_end = min(L, v_begin + seg_len);
             if (v_begin >= v_end) continue;  // empty segment: slot_cnt stays 0
             const int Qt = min(SCAN_QT, cnt_l - qt * SCAN_QT);
-            int q = -1, slot = 0;
+            int slot = 0;
             float tau = 0.f;
+            const int pair0 = rp.list_pair_off[l] + qt * SCAN_QT;
             if (lane < Qt) {
-                unsigned long long pr = rp.pairs[rp.list_pair_off[l] + qt * SCAN_QT + lane];
+                unsigned long long pr = rp.pairs[pair0 + lane];
                 int a = (int)(pr >> 32), p_rel = (int)(pr & 0xffffffffu);
-                q = rp.active[a];
                 slot = (a * rp.w + p_rel) * rp.S + seg;
-                tau = rp.st.tau[q];
+                tau = rp.st.tau[rp.active[a]];
             }
-            const float* qrow = rp.xq + (long long)(q < 0 ? 0 : q) * dpad;
             const int nvec = v_end - v_begin;
             const int nblk = (nvec + SCAN_VT - 1) / SCAN_VT;
             const long long row0 = L0 + v_begin;
@@ -326,10 +338,10 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
                     h->tau[lane] = tau;
                     __syncwarp();
                     if (lane == 0) {
-                        mbar_expect_tx(&full_bar[s], (unsigned)(VT_BYTES + Qt * nk * 4));
+                        mbar_expect_tx(&full_bar[s], (unsigned)(VT_BYTES + QT_BYTES));
                         tma_load_2d(st, &tmap, k0, (int)(row0 + (long long)blk * SCAN_VT), &full_bar[s]);
+                        tma_load_2d(st + VT_BYTES, &qmap, k0, pair0, &full_bar[s]);
                     }
-                    if (lane < Qt) bulk_load(st + VT_BYTES + lane * QLD * 4, qrow + k0, (unsigned)(nk * 4), &full_bar[s]);
                 }
             }
         }
@@ -383,7 +395,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
             const unsigned char* sv = st + lane * 128;
             const float* sq = reinterpret_cast<const float*>(st + VT_BYTES) + warp * 4 * QLD;
             if (nk == SCAN_DK) {
-#pragma unroll
+#pragma unroll 2
                 for (int kc = 0; kc < SCAN_DK / 4; kc++) {
                     float4 a[4], b[4];
 #pragma unroll
@@ -478,7 +490,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-void make_codes_tensor_map(void* out_map, const float* codes, long long nrows, int dpad) {
+static void make_tensor_map_2d(void* out_map, const float* base, long long nrows, int dpad, int box_rows,
+                               bool swizzle) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -489,18 +502,27 @@ void make_codes_tensor_map(void* out_map, const float* codes, long long nrows, i
     }
     cuuint64_t gdim[2] = {(cuuint64_t)dpad, (cuuint64_t)std::max<long long>(nrows, 1)};
     cuuint64_t gstride[1] = {(cuuint64_t)dpad * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)SCAN_DK, (cuuint32_t)SCAN_VT};
+    cuuint32_t box[2] = {(cuuint32_t)SCAN_DK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)codes, gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AUNCEL_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
 }
 
-void launch_scan(const RoundParams& rp, const void* tmap, int num_sms, cudaStream_t s) {
+void make_codes_tensor_map(void* out_map, const float* codes, long long nrows, int dpad) {
+    make_tensor_map_2d(out_map, codes, nrows, dpad, SCAN_VT, true);
+}
+
+void make_queries_tensor_map(void* out_map, const float* xq_sorted, long long nrows, int dpad) {
+    make_tensor_map_2d(out_map, xq_sorted, nrows, dpad, SCAN_QT, false);
+}
+
+void launch_scan(const RoundParams& rp, const void* tmap, const void* qmap, int num_sms, cudaStream_t s) {
     auto kern = rp.metric == METRIC_L2 ? scan_kernel<METRIC_L2> : scan_kernel<METRIC_IP>;
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
-    kern<<<num_sms, THREADS, SCAN_SMEM, s>>>(rp, *reinterpret_cast<const CUtensorMap*>(tmap));
+    kern<<<num_sms, THREADS, SCAN_SMEM, s>>>(rp, *reinterpret_cast<const CUtensorMap*>(tmap),
+                                            *reinterpret_cast<const CUtensorMap*>(qmap));
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -65,6 +65,7 @@ struct RoundParams {
     int* list_tile_off;   // nlist + 1
     int* list_cursor;
     unsigned long long* pairs;
+    float* xq_sorted;     // total_pairs x dpad: query rows in pair order
     int* ctl;
     // pool: slot = (a * w + p_rel) * S + seg, K entries each
     float* cand_d;
@@ -74,7 +75,8 @@ struct RoundParams {
 };
 
 void launch_plan(const RoundParams& rp, cudaStream_t s);
-void launch_scan(const RoundParams& rp, const void* tensor_map, int num_sms, cudaStream_t s);
+void launch_scan(const RoundParams& rp, const void* codes_map, const void* queries_map, int num_sms, cudaStream_t s);
+void make_queries_tensor_map(void* out_map, const float* xq_sorted, long long nrows, int dpad);
 // CUtensorMap (128 B, 64 B aligned) over the list arena [nrows x dpad] f32, box 128 rows x 32 floats
 void make_codes_tensor_map(void* out_map, const float* codes, long long nrows, int dpad);
 
