@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <array>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -146,6 +147,8 @@ struct IvfIndex {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     std::vector<cudaEvent_t> scan_ev;  // pairs of events around every scan launch
     SearchStats stats;
+    bool debug_rounds = false;
+    std::vector<std::array<int, 6>> round_log;
     int num_sms = 148;
 
     IvfIndex(int d, long nlist, int metric, int device);

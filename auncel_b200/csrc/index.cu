@@ -1,5 +1,8 @@
 // IvfIndex: the device-resident IndexIVFFlat and the host side of the query path.
 #include <algorithm>
+#include <array>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "merge.cuh"
@@ -343,6 +346,8 @@ void IvfIndex::search(const QueryBatch& qb) {
         AUNCEL_CHECK(qb.require_acc != nullptr, "require_acc missing");
     }
     stats = SearchStats();
+    round_log.clear();
+    debug_rounds = getenv("AUNCEL_DEBUG_ROUNDS") != nullptr;
     CUDA_CHECK(cudaEventRecord(ev0, stream));
 
     // ---- stage queries (pad rows), coarse ranking
@@ -428,16 +433,22 @@ void IvfIndex::search(const QueryBatch& qb) {
         }
         w = std::min(w, w_cap);
         // segments: split lists when there are too few (list, query-tile) units to fill the GPU
-        long est_tiles = std::min<long>((long)n_active * w, nlist) + (long)n_active * w / SCAN_QT;
+        long est_tiles = std::min<long>((long)n_active * w, nlist) + (long)n_active * w / SCAN_QT;  // lower bound
         long S = (2L * num_sms + est_tiles - 1) / est_tiles;
         S = std::max(1L, std::min<long>(S, 32));
-        while (S > 1 && (size_t)n_active * w * S * K > pool_entries) S--;
+        // narrow tiles (8 queries, rows split over warps) when lists are probed by few queries
+        const double avg_q = (double)n_active * w / (double)std::min<long>(nlist, (long)n_active * w);
+        int nsub = avg_q <= 16.0 ? 4 : 1;
+        if ((size_t)n_active * w * nsub * K > pool_entries) nsub = 1;
+        while (S > 1 && (size_t)n_active * w * S * nsub * K > pool_entries) S--;
+        rp.qt = nsub == 4 ? 8 : SCAN_QT;
+        rp.nsub = nsub;
         rp.active = act_cur;
         rp.n_active = n_active;
         rp.r0 = r0;
         rp.w = (int)w;
         rp.S = (int)S;
-        size_t slots = (size_t)n_active * w * S;
+        size_t slots = (size_t)n_active * w * S * nsub;
         pool.ensure(slots * K * 8);
         rp.cand_d = reinterpret_cast<float*>(pool.p);
         rp.cand_off = reinterpret_cast<unsigned*>(pool.p + slots * K * 4);
@@ -463,6 +474,8 @@ void IvfIndex::search(const QueryBatch& qb) {
         launch_compact_active(rp, r0 + (int)w, act_nxt, h_ctl.p, stream);
         CUDA_CHECK(cudaStreamSynchronize(stream));
         n_active = h_ctl.p[CTL_N_ACTIVE];
+        if (debug_rounds)
+            round_log.push_back({r0, (int)w, (int)S, rp.n_active, h_ctl.p[CTL_TOTAL_TILES], h_ctl.p[CTL_TOTAL_PAIRS]});
         stats.rounds++;
         stats.scan_tiles += (uint64_t)h_ctl.p[CTL_TOTAL_TILES];
         stats.scan_pairs += (uint64_t)h_ctl.p[CTL_TOTAL_PAIRS];
@@ -490,6 +503,10 @@ void IvfIndex::search(const QueryBatch& qb) {
         float t = 0.f;
         CUDA_CHECK(cudaEventElapsedTime(&t, scan_ev[2 * r], scan_ev[2 * r + 1]));
         scan_ms_total += t;
+        if (debug_rounds && r < round_log.size())
+            fprintf(stderr, "[auncel] round %2d r0=%4d w=%4d S=%2d active=%6d tiles=%7d pairs=%8d scan=%8.3f ms\n", (int)r,
+                    round_log[r][0], round_log[r][1], round_log[r][2], round_log[r][3], round_log[r][4],
+                    round_log[r][5], t);
     }
     stats.scan_ms = scan_ms_total;
     stats.scan_launches = stats.rounds;

@@ -151,8 +151,9 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
         const int stage = rp.r0 + p_rel + 1;
         if (stage > bound) break;
         // ---- merge the candidates of probe rank stage-1 (all segments)
-        for (int seg = 0; seg < rp.S; seg++) {
-            const long slot = ((long)a * rp.w + p_rel) * rp.S + seg;
+        const int nseg = rp.S * rp.nsub;
+        for (int seg = 0; seg < nseg; seg++) {
+            const long slot = ((long)a * rp.w + p_rel) * nseg + seg;
             const int c = rp.slot_cnt[slot];
             if (c == 0) continue;
             for (int i = lane; i < KP; i += 32) {

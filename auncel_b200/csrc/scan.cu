@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(1024) plan_offsets_kernel(RoundParams rp) {
     for (long base = 0; base < rp.nlist; base += 1024) {
         long l = base + threadIdx.x;
         int c = l < rp.nlist ? rp.list_cnt[l] : 0;
-        int t = ((c + SCAN_QT - 1) / SCAN_QT) * rp.S;
+        int t = ((c + rp.qt - 1) / rp.qt) * rp.S;
         s_pair[threadIdx.x] = c;
         s_tile[threadIdx.x] = t;
         __syncthreads();
@@ -109,7 +109,7 @@ __global__ void gather_queries_kernel(RoundParams rp) {
 void launch_plan(const RoundParams& rp, cudaStream_t s) {
     long tot = (long)rp.n_active * rp.w;
     CUDA_CHECK(cudaMemsetAsync(rp.list_cnt, 0, rp.nlist * sizeof(int), s));
-    CUDA_CHECK(cudaMemsetAsync(rp.slot_cnt, 0, (size_t)tot * rp.S * sizeof(int), s));
+    CUDA_CHECK(cudaMemsetAsync(rp.slot_cnt, 0, (size_t)tot * rp.S * rp.nsub * sizeof(int), s));
     unsigned blocks = (unsigned)((tot + 255) / 256);
     plan_count_kernel<<<blocks, 256, 0, s>>>(rp);
     plan_offsets_kernel<<<1, 1024, 0, s>>>(rp);
@@ -254,7 +254,11 @@ __device__ __forceinline__ void compact(unsigned long long* buf, int& cnt, float
     __syncwarp();
 }
 
-template <int METRIC>
+// NARROW = false: warp w owns queries 4w..4w+3 and all 128 rows of a block (4 per lane).
+// NARROW = true : tiles hold <= 8 queries; warp w owns queries 4(w/4)..+3 and rows 32(w%4)+lane
+//                 (1 per lane), so a list probed by few queries still keeps all warps busy; the
+//                 four row subsets of a query are written as four sub-slots.
+template <int METRIC, bool NARROW>
 __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap qmap) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES];
@@ -292,7 +296,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
             }
             const int l = lo;
             const int cnt_l = rp.list_pair_off[l + 1] - rp.list_pair_off[l];
-            const int nqt = (cnt_l + SCAN_QT - 1) / SCAN_QT;
+            const int QT = rp.qt;
+            const int nqt = (cnt_l + QT - 1) / QT;
             const int tl = T - rp.list_tile_off[l];
             const int seg = tl / nqt, qt = tl - seg * nqt;
             const long long L0 = rp.list_off[l];
@@ -302,10 +307,10 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
             const int v_begin = seg * seg_len;
             const int v_end = min(L, v_begin + seg_len);
             if (v_begin >= v_end) continue;  // empty segment: slot_cnt stays 0
-            const int Qt = min(SCAN_QT, cnt_l - qt * SCAN_QT);
+            const int Qt = min(QT, cnt_l - qt * QT);
             int slot = 0;
             float tau = 0.f;
-            const int pair0 = rp.list_pair_off[l] + qt * SCAN_QT;
+            const int pair0 = rp.list_pair_off[l] + qt * QT;
             if (lane < Qt) {
                 unsigned long long pr = rp.pairs[pair0 + lane];
                 int a = (int)(pr >> 32), p_rel = (int)(pr & 0xffffffffu);
@@ -359,13 +364,16 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
     }
 
     // =========================== consumers ===========================
+    constexpr int TV = NARROW ? 1 : 4;                 // list rows per lane
+    const int qbase = NARROW ? (warp >> 2) * 4 : warp * 4;  // first query of this warp
+    const int rbase = NARROW ? (warp & 3) * 32 : 0;    // first row of this warp (rows rbase + lane + 32 j)
     int cnt[4] = {0, 0, 0, 0};
     float tau[4] = {0.f, 0.f, 0.f, 0.f};
-    float acc[4][4][4];
+    float acc[4][TV][4];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+        for (int j = 0; j < TV; j++)
 #pragma unroll
             for (int x = 0; x < 4; x++) acc[i][j][x] = 0.f;
     const int xr = lane & 7;  // SWIZZLE_128B: 16-byte chunk index is XORed with (row & 7)
@@ -377,50 +385,36 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
         const StageHdr* h = reinterpret_cast<const StageHdr*>(st + VT_BYTES + QT_BYTES);
         if (h->flags) break;
         const int Qt = h->Qt;
-        const bool has_q = warp * 4 < Qt;
+        const bool has_q = qbase < Qt;
         const int last_chunk = h->last_chunk, last_iter = h->last_iter;
         const int blk = h->blk, nvec = h->nvec, v_begin = h->v_begin, nk = h->nk;
         int slot[4];
         if (h->first) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                tau[i] = h->tau[warp * 4 + i];
+                tau[i] = h->tau[qbase + i];
                 cnt[i] = 0;
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) slot[i] = h->slot[warp * 4 + i];
+        for (int i = 0; i < 4; i++) slot[i] = h->slot[qbase + i];
 
         if (has_q) {
-            const unsigned char* sv = st + lane * 128;
-            const float* sq = reinterpret_cast<const float*>(st + VT_BYTES) + warp * 4 * QLD;
-            if (nk == SCAN_DK) {
+            const unsigned char* sv = st + (rbase + lane) * 128;
+            const float* sq = reinterpret_cast<const float*>(st + VT_BYTES) + qbase * QLD;
+            const int nkc = nk >> 2;
 #pragma unroll 2
-                for (int kc = 0; kc < SCAN_DK / 4; kc++) {
-                    float4 a[4], b[4];
+            for (int kc = 0; kc < nkc; kc++) {
+                float4 a[4], b[TV];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4*>(sq + i * QLD + kc * 4);
+                for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4*>(sq + i * QLD + kc * 4);
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        b[j] = *reinterpret_cast<const float4*>(sv + j * (32 * 128) + ((kc ^ xr) << 4));
+                for (int j = 0; j < TV; j++)
+                    b[j] = *reinterpret_cast<const float4*>(sv + j * (32 * 128) + ((kc ^ xr) << 4));
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
+                for (int i = 0; i < 4; i++)
 #pragma unroll
-                        for (int j = 0; j < 4; j++) exact_step<METRIC>(acc[i][j], a[i], b[j]);
-                }
-            } else {
-                for (int kc = 0; kc < nk / 4; kc++) {
-                    float4 a[4], b[4];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4*>(sq + i * QLD + kc * 4);
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        b[j] = *reinterpret_cast<const float4*>(sv + j * (32 * 128) + ((kc ^ xr) << 4));
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-#pragma unroll
-                        for (int j = 0; j < 4; j++) exact_step<METRIC>(acc[i][j], a[i], b[j]);
-                }
+                    for (int j = 0; j < TV; j++) exact_step<METRIC>(acc[i][j], a[i], b[j]);
             }
         }
         // the stage's data and header are consumed: hand the slot back to the producer
@@ -432,12 +426,12 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 unsigned long long* buf = cand + (size_t)(warp * 4 + i) * CAP;
-                const bool qok = warp * 4 + i < Qt;
+                const bool qok = qbase + i < Qt;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
+                for (int j = 0; j < TV; j++) {
                     float dist = exact_finish(acc[i][j]);
                     acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
-                    int v = blk * SCAN_VT + lane + 32 * j;
+                    int v = blk * SCAN_VT + rbase + lane + 32 * j;
                     bool pass = qok && v < nvec && (METRIC == METRIC_L2 ? dist < tau[i] : dist > tau[i]);
                     unsigned m = __ballot_sync(0xffffffffu, pass);
                     if (m) {
@@ -454,12 +448,12 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
             }
         }
         if (has_q && last_iter) {
-            // ---- per-(query, segment) result: sorted, at most K candidates
+            // ---- per-(query, segment[, row subset]) result: sorted, at most K candidates
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                if (warp * 4 + i < Qt && cnt[i] > 0) {
+                if (qbase + i < Qt && cnt[i] > 0) {
                     unsigned long long* buf = cand + (size_t)(warp * 4 + i) * CAP;
-                    const long sl = slot[i];
+                    const long sl = NARROW ? (long)slot[i] * 4 + (warp & 3) : (long)slot[i];
                     if (cnt[i] <= 32) {
                         unsigned long long key = lane < cnt[i] ? buf[lane] : ~0ull;
                         key = warp_sort_reg(key, lane);
@@ -519,7 +513,8 @@ void make_queries_tensor_map(void* out_map, const float* xq_sorted, long long nr
 }
 
 void launch_scan(const RoundParams& rp, const void* tmap, const void* qmap, int num_sms, cudaStream_t s) {
-    auto kern = rp.metric == METRIC_L2 ? scan_kernel<METRIC_L2> : scan_kernel<METRIC_IP>;
+    auto kern = rp.metric == METRIC_L2 ? (rp.nsub == 4 ? scan_kernel<METRIC_L2, true> : scan_kernel<METRIC_L2, false>)
+                                       : (rp.nsub == 4 ? scan_kernel<METRIC_IP, true> : scan_kernel<METRIC_IP, false>);
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
     kern<<<num_sms, THREADS, SCAN_SMEM, s>>>(rp, *reinterpret_cast<const CUtensorMap*>(tmap),
                                             *reinterpret_cast<const CUtensorMap*>(qmap));

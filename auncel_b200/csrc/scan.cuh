@@ -59,6 +59,8 @@ struct RoundParams {
     const int* active;    // n_active -> query
     int n_active;
     int r0, w, S;
+    int qt;               // queries per scan tile this round: 32 (wide) or 8 (narrow)
+    int nsub;             // sub-slots per (query, rank, segment): 4 in narrow rounds, else 1
     // plan
     int* list_cnt;
     int* list_pair_off;   // nlist + 1
@@ -67,7 +69,7 @@ struct RoundParams {
     unsigned long long* pairs;
     float* xq_sorted;     // total_pairs x dpad: query rows in pair order
     int* ctl;
-    // pool: slot = (a * w + p_rel) * S + seg, K entries each
+    // pool: slot = ((a * w + p_rel) * S + seg) * nsub + sub, K entries each
     float* cand_d;
     unsigned* cand_off;
     int* slot_cnt;
