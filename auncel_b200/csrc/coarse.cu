@@ -145,8 +145,10 @@ void launch_interdis(int metric, const float* cent, long nlist, int dpad, float*
 // distances rank by centroid id.
 __global__ void __launch_bounds__(1024)
 rank_rows_kernel(int metric, const float* __restrict__ dis, long nlist, int P, float* __restrict__ out_dis,
-                 int* __restrict__ out_keys) {
+                 int* __restrict__ out_keys, int* __restrict__ tie0) {
     extern __shared__ unsigned long long skey[];
+    __shared__ int s_tie;
+    if (threadIdx.x == 0) s_tie = 0x7fffffff;
     const long q = blockIdx.x;
     const float* row = dis + q * nlist;
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
@@ -180,11 +182,144 @@ rank_rows_kernel(int metric, const float* __restrict__ dis, long nlist, int P, f
         if (metric == METRIC_IP) o = ~o;
         out_dis[q * nlist + i] = ord2f(o);
         out_keys[q * nlist + i] = (int)(key & 0xffffffffu);
+        // equal distances: the reference's order among them is whatever its heap produces
+        if (i + 1 < nlist && (uint32_t)(skey[i + 1] >> 32) == (uint32_t)(key >> 32)) atomicMin(&s_tie, i);
     }
+    __syncthreads();
+    if (threadIdx.x == 0) tie0[q] = s_tie;
+}
+
+// ---------------------------------------------------------------------------------
+// Exact tie order.  IndexFlat::search ranks centroids with a binary heap of size k (= nprobe;
+// nlist in Auncel mode): knn_L2sqr_sse / knn_inner_product_sse (utils.cpp:417-490) push every
+// candidate that beats the heap top, then heap_reorder (Heap.h:295-322) pops them out.  Among
+// EQUAL distances the output order is a by-product of the heap's layout -- and with thousands
+// of centroids at float resolution ties are common (birthday effect).  The probe order decides
+// what the termination check sees at each stage, so for the queries that have a tie inside
+// the range that matters the heap is replayed literally: one thread walks the reference's
+// algorithm in shared memory (Heap.h:88-142).
+// Heap nodes are packed as (ord << 32 | id) with ord = f2ord(dis) for L2 (CMax: a > b) and
+// ~f2ord(sim) for IP (CMin: a < b), so both metrics are a max-heap on ord; comparisons look at
+// ord only -- ids never break ties, exactly like the reference's cmp on values.
+__device__ __forceinline__ bool ngt(unsigned long long a, unsigned long long b) {
+    return (uint32_t)(a >> 32) > (uint32_t)(b >> 32);
+}
+
+// Heap.h:88-117 on a 1-based array
+__device__ __forceinline__ void heap_pop_dev(int k, unsigned long long* h) {
+    const unsigned long long v = h[k];
+    int i = 1;
+    while (true) {
+        const int i1 = i << 1, i2 = i1 + 1;
+        if (i1 > k) break;
+        const unsigned long long c1 = h[i1], c2 = h[i2 <= k ? i2 : i1];
+        const bool left = (i2 == k + 1) || ngt(c1, c2);
+        const unsigned long long c = left ? c1 : c2;
+        if (ngt(v, c)) break;
+        h[i] = c;
+        i = left ? i1 : i2;
+    }
+    h[i] = v;
+}
+
+// Heap.h:124-142
+__device__ __forceinline__ void heap_push_dev(int k, unsigned long long* h, unsigned long long v) {
+    int i = k;
+    while (i > 1) {
+        const int f = i >> 1;
+        const unsigned long long p = h[f];
+        if (!ngt(v, p)) break;
+        h[i] = p;
+        i = f;
+    }
+    h[i] = v;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(32)
+heap_order_kernel(const float* __restrict__ raw, long nlist, int k, const int* __restrict__ fix_list,
+                  const int* __restrict__ nfix, float* __restrict__ out_dis, int* __restrict__ out_keys,
+                  int* __restrict__ tie0) {
+    if ((int)blockIdx.x >= *nfix) return;
+    extern __shared__ unsigned long long hp[];  // k nodes, used 1-based through h = hp - 1
+    unsigned long long* h = hp - 1;
+    const long q = fix_list[blockIdx.x];
+    const int lane = threadIdx.x;
+    const float neut = METRIC == METRIC_L2 ? FLT_MAX : -FLT_MAX;
+    uint32_t on = f2ord(neut);
+    if (METRIC == METRIC_IP) on = ~on;
+    for (int i = lane; i < k; i += 32) hp[i] = ((unsigned long long)on << 32) | 0xffffffffu;  // heapify, id -1
+    __syncwarp();
+    if (lane == 0) {
+        const float* row = raw + q * nlist;
+        constexpr int PF = 8;  // software prefetch of the distance row
+        float buf[PF];
+#pragma unroll
+        for (int t = 0; t < PF; t++) buf[t] = t < nlist ? __ldg(row + t) : 0.f;
+        for (long j0 = 0; j0 < nlist; j0 += PF) {
+            float cur[PF];
+#pragma unroll
+            for (int t = 0; t < PF; t++) {
+                cur[t] = buf[t];
+                long nj = j0 + PF + t;
+                buf[t] = nj < nlist ? __ldg(row + nj) : 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < PF; t++) {
+                long j = j0 + t;
+                if (j >= nlist) break;
+                uint32_t o = f2ord(cur[t]);
+                if (METRIC == METRIC_IP) o = ~o;
+                if (o < (uint32_t)(h[1] >> 32)) {  // dis < simi[0] (L2) / ip > simi[0] (IP), utils.cpp:441,479
+                    heap_pop_dev(k, h);
+                    heap_push_dev(k, h, ((unsigned long long)o << 32) | (unsigned)j);
+                }
+            }
+        }
+        // heap_reorder, Heap.h:295-322 (every slot holds a real element because k <= nlist)
+        for (int i = 0; i < k; i++) {
+            const unsigned long long top = h[1];
+            heap_pop_dev(k - i, h);
+            h[k - i] = top;  // slot k-i is free after the pop: same as bh_val[k-ii-1] with ii == i
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < k; i += 32) {
+        const unsigned long long node = hp[i];
+        uint32_t o = (uint32_t)(node >> 32);
+        if (METRIC == METRIC_IP) o = ~o;
+        out_dis[q * nlist + i] = ord2f(o);
+        out_keys[q * nlist + i] = (int)(uint32_t)(node & 0xffffffffu);
+    }
+    if (lane == 0) tie0[q] = 0x7fffffff;
+}
+
+// queries (from `list`, or all n when list == nullptr) whose first tie lies below `bound`
+__global__ void collect_ties_kernel(const int* __restrict__ list, int n, const int* __restrict__ tie0, int bound,
+                                    const int* __restrict__ qbound, int* __restrict__ fix_list,
+                                    int* __restrict__ nfix) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    int q = list ? list[a] : a;
+    int b = qbound ? min(bound, qbound[q]) : bound;  // a decided query never scans past its stop stage
+    if (tie0[q] < b) fix_list[atomicAdd(nfix, 1)] = q;
+}
+
+void launch_fix_ties(int metric, const float* raw, long nlist, int k, const int* list, int n, int* tie0, int bound,
+                     const int* qbound, int* fix_list, int* nfix, float* out_dis, int* out_keys, cudaStream_t s) {
+    if (n == 0) return;
+    CUDA_CHECK(cudaMemsetAsync(nfix, 0, sizeof(int), s));
+    collect_ties_kernel<<<(n + 255) / 256, 256, 0, s>>>(list, n, tie0, bound, qbound, fix_list, nfix);
+    size_t smem = (size_t)k * 8;
+    AUNCEL_CHECK(smem <= 220 * 1024, "nlist too large for the exact tie replay");
+    auto kern = metric == METRIC_L2 ? heap_order_kernel<METRIC_L2> : heap_order_kernel<METRIC_IP>;
+    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<n, 32, smem, s>>>(raw, nlist, k, fix_list, nfix, out_dis, out_keys, tie0);
+    CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_rank_rows(int metric, const float* dis, long nq, long nlist, float* out_dis, int* out_keys,
-                      cudaStream_t s) {
+                      int* tie0, cudaStream_t s) {
     if (nq == 0) return;
     int P = 1;
     while (P < nlist) P <<= 1;
@@ -193,7 +328,7 @@ void launch_rank_rows(int metric, const float* dis, long nq, long nlist, float* 
     if (smem > 48 * 1024)
         CUDA_CHECK(cudaFuncSetAttribute(rank_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int threads = std::max(32, std::min(1024, P / 2));
-    rank_rows_kernel<<<(unsigned)nq, threads, smem, s>>>(metric, dis, nlist, P, out_dis, out_keys);
+    rank_rows_kernel<<<(unsigned)nq, threads, smem, s>>>(metric, dis, nlist, P, out_dis, out_keys, tie0);
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -312,13 +312,16 @@ ErrModelView IvfIndex::model_view() const {
 void IvfIndex::coarse_rank(long n, const float* xs /* n x dpad, device */) {
     c_dis.ensure((size_t)n * nlist);
     c_keys.ensure((size_t)n * nlist);
-    DevBuf<float>& raw = c_raw;
+    c_tie0.ensure(n);
+    fix_list.ensure(n);
+    DevBuf<float>& raw = c_raw;  // kept for the whole search: the tie replay reads it
     const long chunk = 65535L * 64;
-    raw.ensure((size_t)std::min(n, chunk) * nlist);
+    raw.ensure((size_t)n * nlist);
     for (long i0 = 0; i0 < n; i0 += chunk) {
         long m = std::min(chunk, n - i0);
-        launch_coarse_distances(metric, xs + i0 * dpad, m, centroids.p, nlist, dpad, raw.p, nullptr, stream);
-        launch_rank_rows(metric, raw.p, m, nlist, c_dis.p + i0 * nlist, c_keys.p + i0 * nlist, stream);
+        launch_coarse_distances(metric, xs + i0 * dpad, m, centroids.p, nlist, dpad, raw.p + i0 * nlist, nullptr, stream);
+        launch_rank_rows(metric, raw.p + i0 * nlist, m, nlist, c_dis.p + i0 * nlist, c_keys.p + i0 * nlist,
+                         c_tie0.p + i0, stream);
     }
 }
 
@@ -401,6 +404,9 @@ void IvfIndex::search(const QueryBatch& qb) {
     tp.max_num = max_num();
     tp.snapshots = qb.snapshots;
     tp.n_traces = expected_traces();
+    if (qb.mode != 0 && exact_ties)  // set_online reads ranks 0..max_num
+        launch_fix_ties(metric, c_raw.p, nlist, nprobe, nullptr, (int)n, c_tie0.p, tp.max_num + 1, nullptr, fix_list.p,
+                        ctl.p + CTL_NFIX, c_dis.p, c_keys.p, stream);
     if (qb.mode != 0) {
         float* dtb_p = qb.dtb_out ? qb.dtb_out : dtb.ensure((size_t)n * tp.max_num);
         launch_set_online(metric, nlist, n, c_dis.p, c_keys.p, interdis.p, d_arcos.p, (int)h_arcos.size(), dtb_p,
@@ -465,12 +471,15 @@ void IvfIndex::search(const QueryBatch& qb) {
             scan_ev.push_back(a);
             scan_ev.push_back(b);
         }
+        if (exact_ties)  // ranks [r0, r0+w) are about to be scanned: their order must be the reference's
+            launch_fix_ties(metric, c_raw.p, nlist, nprobe, act_cur, n_active, c_tie0.p, r0 + (int)w, rp.st.bound, fix_list.p,
+                            ctl.p + CTL_NFIX, c_dis.p, c_keys.p, stream);
         launch_plan(rp, stream);
         CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds], stream));
         launch_scan(rp, codes_tmap, qmap, num_sms, stream);
         CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds + 1], stream));
         launch_merge_check(rp, tp, stream);
-        launches += 7;  // plan x3, gather, scan, merge_check, compact_active
+        launches += 7 + (exact_ties ? 2 : 0);  // [collect_ties, heap_order,] plan x3, gather, scan, merge_check, compact_active
         launch_compact_active(rp, r0 + (int)w, act_nxt, h_ctl.p, stream);
         CUDA_CHECK(cudaStreamSynchronize(stream));
         n_active = h_ctl.p[CTL_N_ACTIVE];

@@ -186,3 +186,58 @@ def test_train_kmeans_runs_and_searches():
     assert np.array_equal(orc.interdis, ix.interdis_cem())
     sizes = ix.list_sizes()
     assert sizes.sum() == 20000 and (sizes > 0).mean() > 0.9
+
+
+def _lattice(seed, n, d, levels=3):
+    """small-integer coordinates: squared distances are small integers -> ties everywhere"""
+    return np.floor(synth.uniform(seed, (n, d)) * levels).astype(np.float32)
+
+
+@pytest.mark.parametrize("metric", [O.L2, O.IP])
+def test_coarse_ties_follow_reference_heap_order(metric):
+    """Equal coarse distances: the reference's probe order is its heap's pop order
+    (utils.cpp:417-490 + Heap.h:295-322); the GPU replays it (coarse.cu heap_order_kernel)."""
+    d, nlist = 8, 256
+    cent = _lattice(1, nlist, d, 4)
+    xq = _lattice(2, 64, d, 4)
+    orc = O.OracleIndex(d, nlist, metric)
+    orc.centroids = cent
+    ix = ab.IndexIVFFlat(d, nlist, metric)
+    ix.set_centroids(cent, compute_interdis=False)
+    for nprobe in (1, 7, 64, 256):
+        dis, keys = ix.coarse_search(xq, nprobe)
+        odis, okeys = orc.coarse(xq, nprobe)
+        assert np.array_equal(dis, odis)
+        assert np.array_equal(keys, okeys), nprobe
+        assert (odis[:, 1:] == odis[:, :-1]).any() or nprobe == 1
+
+
+def test_bounded_search_with_coarse_ties():
+    """my_nprobe parity when many centroids are equidistant from the query."""
+    d, nlist, nb, k, qk = 8, 64, 6000, 16, 4
+    cent = _lattice(3, nlist, d, 5) + 0.25 * synth.clustered(4, nlist, d, 10, 0.05)
+    cent = np.round(cent * 4) / 4  # quarter-integer grid: still many exact ties
+    xb = (_lattice(5, nb, d, 5) + 0.01 * synth.clustered(6, nb, d, 10, 0.3)).astype(np.float32)
+    xq = _lattice(7, 200, d, 5)
+    orc = O.OracleIndex(d, nlist, O.L2)
+    orc.set_centroids(cent)
+    orc.add(xb)
+    ix = ab.IndexIVFFlat(d, nlist, O.L2)
+    ix.set_centroids(cent)
+    ix.add(xb, )
+    assert np.array_equal(ix.assign(xb), orc.assign(xb))
+    cd, ck = orc.coarse(xq, nlist)
+    assert (cd[:, 1:] == cd[:, :-1]).any(1).mean() > 0.5
+    gD, gI = orc.search_fixed(xq, k, nlist)
+    orc.calibrate(xq[:100], gD[:100])
+    ix.set_error_model(orc.traces, 1.5, 1.0)
+    orc.multipler, orc.std_m = 1.5, 1.0
+    acc = np.full(200, 0.9, np.float32)
+    D2, I2, np2, _ = orc.search_bounded(xq[100:], k, qk, acc, offset=100)
+    D1, I1, np1 = ix.search_bounded(xq[100:], k, qk, acc[100:])
+    assert np.array_equal(np1, np2[100:])
+    assert np.array_equal(D1, D2)
+    ix.nprobe = 5
+    D, I = ix.search(xq, k)
+    D2, I2 = orc.search_fixed(xq, k, 5)
+    assert np.array_equal(D, D2)
