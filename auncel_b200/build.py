@@ -45,6 +45,19 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_examples():
+    """C++ driver written against include/auncel/faiss_api.h (the reference-API mirror)."""
+    root = os.path.dirname(HERE)
+    out = os.path.join(root, "examples", "bound_demo")
+    src = os.path.join(root, "examples", "bound_demo.cpp")
+    hdrs = [os.path.join(root, "include", "auncel", "faiss_api.h"), os.path.join(root, "include", "auncel_b200.h")]
+    if os.path.exists(out) and all(os.path.getmtime(out) > os.path.getmtime(f) for f in [src, LIB] + hdrs):
+        return out
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++14", "-I", os.path.join(root, "include"), src, "-o", out,
+                           LIB, "-Wl,-rpath," + HERE, "-lpthread"])
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(LIB)

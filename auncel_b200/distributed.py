@@ -1,0 +1,114 @@
+"""Multi-GPU wrappers: one process per GPU, torch.distributed for the plumbing.
+
+* ReplicaGroup -- IndexReplicas semantics (/root/reference/Auncel/IndexReplicas.cpp:79-118):
+  every rank holds the whole index, the query batch is cut into contiguous chunks of
+  ceil(n / world), results land in disjoint row ranges.  No data-path collective.
+* ShardGroup -- IndexShards semantics (IndexShards.cpp:261-311) with a shared quantizer and
+  every inverted list split over the ranks (copy_subset_to type 1/2, IndexIVF.cpp:1055-1118,
+  the way gpu/GpuAutoTune.cpp:201-220 clones an index over GPUs): every rank searches all
+  queries in its shard, one all_gather of the (n x k) distance / label tables over
+  NCCL/NVLink, then merge_tables (IndexShards.cpp:44-105) on the device.
+
+The index object only needs `search_device(x_t, k, D_t, I_t)` / `search(x, k)`, so the CPU
+tests drive these classes with a recording mock (tests/test_threaded_index.cpp style) over gloo.
+"""
+import numpy as np
+
+
+def replica_slice(n, world, rank):
+    """IndexReplicas.cpp:95-112: queriesPerIndex = ceil(n / count); base = i * queriesPerIndex."""
+    per = (n + world - 1) // world
+    base = rank * per
+    return base, max(0, min(per, n - base))
+
+
+def shard_mask(ids, world, rank, subset_type=1, ntotal=None):
+    """Which vectors rank `rank` owns. type 1: id % world == rank (IndexIVF.cpp:1086-1095)."""
+    ids = np.asarray(ids)
+    if subset_type == 1:
+        return ids % world == rank
+    raise ValueError("subset types other than 1 are list-local; use IndexIVFFlat.copy_subset_to")
+
+
+class ReplicaGroup:
+    def __init__(self, index, group=None):
+        import torch.distributed as dist
+        self.index, self.group, self.dist = index, group, dist
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def search(self, x, k):
+        """x: the full (n, d) host batch, identical on every rank. Returns this rank's rows
+        (base, D, I); nothing is exchanged."""
+        base, m = replica_slice(len(x), self.world, self.rank)
+        if m == 0:
+            return base, np.zeros((0, k), np.float32), np.zeros((0, k), np.int64)
+        D, I = self.index.search(x[base:base + m], k)
+        return base, D, I
+
+    def search_gathered(self, x, k):
+        """Same, then all ranks assemble the full (n, k) tables (what IndexReplicas::search
+        leaves in the caller's buffers)."""
+        import torch
+        n = len(x)
+        base, D, I = self.search(x, k)
+        per = (n + self.world - 1) // self.world
+        Dp = torch.full((per, k), np.nan, dtype=torch.float32)
+        Ip = torch.full((per, k), -1, dtype=torch.int64)
+        Dp[:len(D)] = torch.from_numpy(D)
+        Ip[:len(I)] = torch.from_numpy(I)
+        if self.world == 1:
+            return D, I
+        Dall = [torch.empty_like(Dp) for _ in range(self.world)]
+        Iall = [torch.empty_like(Ip) for _ in range(self.world)]
+        self.dist.all_gather(Dall, Dp, group=self.group)
+        self.dist.all_gather(Iall, Ip, group=self.group)
+        return torch.cat(Dall)[:n].numpy(), torch.cat(Iall)[:n].numpy()
+
+
+class ShardGroup:
+    def __init__(self, index, metric, group=None, translations=None, merge_fn=None, device=None):
+        import torch.distributed as dist
+        self.index, self.metric, self.group, self.dist = index, metric, group, dist
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.translations = translations  # successive_ids shifts, IndexShards.cpp:289-297
+        self.merge_fn = merge_fn
+        self.device = device
+
+    def _merge_device(self, allD, allI, n, k):
+        import torch
+
+        from ._lib import lib
+        from .index import _ck
+        D = torch.empty(n, k, device=allD.device, dtype=torch.float32)
+        I = torch.empty(n, k, device=allD.device, dtype=torch.int64)
+        tr = None
+        if self.translations is not None:
+            tr = torch.as_tensor(self.translations, dtype=torch.int64, device=allD.device)
+        stream = torch.cuda.current_stream(allD.device).cuda_stream
+        _ck(lib().auncel_merge_tables_device(allD.device.index, self.metric, n, k, self.world, allD.data_ptr(),
+                                             allI.data_ptr(), None if tr is None else tr.data_ptr(),
+                                             D.data_ptr(), I.data_ptr(), stream))
+        return D, I
+
+    def search_device(self, x_t, k):
+        """x_t: (n, d) tensor, identical on every rank (CUDA for NCCL, CPU for gloo tests).
+        Every rank returns the merged (n, k) tables."""
+        import torch
+        n = x_t.shape[0]
+        D = torch.empty(n, k, device=x_t.device, dtype=torch.float32)
+        I = torch.empty(n, k, device=x_t.device, dtype=torch.int64)
+        self.index.search_device(x_t, k, D, I)
+        if x_t.is_cuda:
+            torch.cuda.current_stream(x_t.device).synchronize()  # the library ran on its own stream
+        if self.world == 1:
+            allD, allI = D[None], I[None]
+        else:
+            allD = torch.empty(self.world, n, k, device=x_t.device, dtype=torch.float32)
+            allI = torch.empty(self.world, n, k, device=x_t.device, dtype=torch.int64)
+            self.dist.all_gather_into_tensor(allD.view(self.world * n, k), D, group=self.group)
+            self.dist.all_gather_into_tensor(allI.view(self.world * n, k), I, group=self.group)
+        if self.merge_fn is not None:
+            return self.merge_fn(self.metric, allD, allI, self.translations)
+        return self._merge_device(allD, allI, n, k)

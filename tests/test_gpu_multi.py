@@ -1,0 +1,65 @@
+"""GPU, >= 2 devices: shards (NCCL all_gather + device merge_tables) equal the single index
+(tests/test_merge.cpp invariant); replicas answer disjoint query slices identically."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")]
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    import auncel_b200 as ab
+    from auncel_b200 import distributed as AD
+    from auncel_b200 import synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        d, nlist, nb, k = 24, 64, 20000, 10
+        xb = synth.clustered(3, nb, d, 30)
+        cent = synth.clustered(53, nlist, d, 30)
+        xq = synth.clustered(21, 300, d, 30)
+        ids = np.arange(nb, dtype=np.int64)
+        full = ab.IndexIVFFlat(d, nlist, ab.METRIC_L2, device=rank)
+        full.set_centroids(cent)
+        full.add(xb)
+        full.nprobe = 6
+        Dref, Iref = full.search(xq, k)
+        # shard: the vectors with id % world == rank, same centroids (copy_subset_to type 1)
+        mine = AD.shard_mask(ids, world, rank)
+        shard = ab.IndexIVFFlat(d, nlist, ab.METRIC_L2, device=rank)
+        shard.set_centroids(cent, compute_interdis=False)
+        shard.add_with_ids(xb[mine], ids[mine])
+        shard.nprobe = 6
+        sg = AD.ShardGroup(shard, ab.METRIC_L2)
+        xq_t = torch.from_numpy(xq).cuda(rank)
+        D, I = sg.search_device(xq_t, k)
+        torch.cuda.synchronize()
+        assert np.array_equal(D.cpu().numpy(), Dref)
+        assert (I.cpu().numpy() == Iref).mean() > 0.999
+        # replicas
+        rg = AD.ReplicaGroup(full)
+        base, Dr, Ir = rg.search(xq, k)
+        assert np.array_equal(Dr, Dref[base:base + len(Dr)]) and np.array_equal(Ir, Iref[base:base + len(Ir)])
+        Dg, Ig = rg.search_gathered(xq, k)
+        assert np.array_equal(Dg, Dref)
+        out[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shards_and_replicas_two_gpus():
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    assert dict(out) == {0: "ok", 1: "ok"}

@@ -241,3 +241,15 @@ def test_bounded_search_with_coarse_ties():
     D, I = ix.search(xq, k)
     D2, I2 = orc.search_fixed(xq, k, 5)
     assert np.array_equal(D, D2)
+
+
+def test_cpp_api_mirror_demo():
+    """examples/bound_demo.cpp: the reference-API mirror (include/auncel/faiss_api.h) end to end."""
+    import os
+    import subprocess
+    from auncel_b200 import build as b
+    exe = b.build_examples()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600, cwd=os.path.dirname(exe))
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "DEMO OK" in r.stdout
+    assert "Error bound is guaranteed" in r.stdout
