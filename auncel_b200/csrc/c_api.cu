@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <random>
 #include <utility>
 
@@ -18,7 +19,12 @@ struct AuncelIndex_H {
     DevBuf<float> x, D, acc, gt, trec, snap, dtbo;
     DevBuf<long long> I;
     DevBuf<unsigned long long> np;
+    // Index::search is const and callable from several threads in the reference (IndexReplicas /
+    // IndexShards worker threads); calls on one handle share its stream and scratch, so they are
+    // serialised here.
+    std::recursive_mutex mu;
 };
+#define LOCK(idx) std::lock_guard<std::recursive_mutex> lock_((idx)->mu)
 
 static thread_local std::string g_last_error;
 
@@ -302,28 +308,33 @@ int auncel_index_is_trained(const AuncelIndex* idx) { return idx->ix.trained ? 1
 
 int auncel_index_set_centroids(AuncelIndex* idx, const float* centroids, int compute_interdis) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     AUNCEL_CHECK(centroids != nullptr, "null centroids");
     idx->ix.set_centroids(centroids, compute_interdis != 0);
     API_CATCH
 }
 int auncel_index_get_centroids(const AuncelIndex* idx, float* out) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     idx->ix.get_centroids(out);
     API_CATCH
 }
 int auncel_index_get_interdis(const AuncelIndex* idx, float* out) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     idx->ix.get_interdis(out);
     API_CATCH
 }
 int auncel_index_set_interdis(AuncelIndex* idx, const float* in) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     idx->ix.set_interdis(in);
     API_CATCH
 }
 
 int auncel_index_train(AuncelIndex* idx, int64_t n, const float* x, int niter, int tune) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     train_kmeans(idx, (long)n, x, niter > 0 ? niter : 25, tune != 0);  // cp.niter = 25, IndexIVF.cpp:54
     API_CATCH
 }
@@ -331,12 +342,14 @@ int auncel_index_train(AuncelIndex* idx, int64_t n, const float* x, int niter, i
 int auncel_index_add_device(AuncelIndex* idx, int64_t n, const float* x_dev, const int64_t* ids,
                             const int64_t* list_no) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     idx->ix.add_device((long)n, x_dev, (const long long*)ids, (const long long*)list_no);
     API_CATCH
 }
 
 int auncel_index_add(AuncelIndex* idx, int64_t n, const float* x, const int64_t* ids, const int64_t* list_no) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     IvfIndex& ix = idx->ix;
     CUDA_CHECK(cudaSetDevice(ix.device));
     const long bs = 1L << 22;  // bounded staging; order of appends is preserved
@@ -352,6 +365,7 @@ int auncel_index_add(AuncelIndex* idx, int64_t n, const float* x, const int64_t*
 
 int auncel_index_assign(AuncelIndex* idx, int64_t n, const float* x, int64_t* list_no) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     IvfIndex& ix = idx->ix;
     CUDA_CHECK(cudaSetDevice(ix.device));
     idx->x.ensure((size_t)n * ix.d);
@@ -362,6 +376,7 @@ int auncel_index_assign(AuncelIndex* idx, int64_t n, const float* x, int64_t* li
 
 int auncel_index_reset(AuncelIndex* idx) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     idx->ix.reset();
     API_CATCH
 }
@@ -383,6 +398,7 @@ __global__ void widen_keys_kernel(const float* dis, const int* keys, long n, lon
 int auncel_index_coarse_search(AuncelIndex* idx, int64_t n, const float* x, int64_t nprobe, float* coarse_dis,
                                int64_t* keys) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     IvfIndex& ix = idx->ix;
     CUDA_CHECK(cudaSetDevice(ix.device));
     AUNCEL_CHECK(ix.trained, "index is not trained");
@@ -413,6 +429,7 @@ int auncel_index_coarse_search(AuncelIndex* idx, int64_t n, const float* x, int6
 int auncel_index_search_device(AuncelIndex* idx, int64_t n, const float* x_dev, int64_t k, int64_t nprobe,
                                int64_t max_codes, float* distances_dev, int64_t* labels_dev) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     QueryBatch qb;
     qb.n = (long)n;
     qb.x = x_dev;
@@ -429,6 +446,7 @@ int auncel_index_search_device(AuncelIndex* idx, int64_t n, const float* x_dev, 
 int auncel_index_search(AuncelIndex* idx, int64_t n, const float* x, int64_t k, int64_t nprobe, int64_t max_codes,
                         float* distances, int64_t* labels) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     IvfIndex& ix = idx->ix;
     CUDA_CHECK(cudaSetDevice(ix.device));
     AUNCEL_CHECK(k >= 1 && k <= MAX_K, "k must be in [1, 128]");
@@ -455,6 +473,7 @@ int auncel_index_search(AuncelIndex* idx, int64_t n, const float* x, int64_t k, 
 int auncel_index_set_error_model(AuncelIndex* idx, int n_traces, const int64_t* trace_off, const float* phi,
                                  const float* U, const float* sigma, float multipler, float std_m) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     std::vector<long> off(trace_off, trace_off + n_traces + 1);
     idx->ix.set_error_model(500, n_traces, off.data(), phi, U, sigma, multipler, std_m);
     API_CATCH
@@ -484,6 +503,7 @@ int auncel_index_get_trace(const AuncelIndex* idx, int t, float* phi, float* U, 
 int auncel_index_calibrate(AuncelIndex* idx, int64_t n, const float* x, int64_t max_topk, const float* gt_D,
                            float* distances, int64_t* labels) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     AUNCEL_CHECK(n > 0 && x && gt_D, "calibration needs queries and their ground-truth distances");
     calibrate(idx, (long)n, x, (int)max_topk, gt_D, distances, (long long*)labels);
     API_CATCH
@@ -494,6 +514,7 @@ int auncel_index_search_bounded_device(AuncelIndex* idx, int64_t n, const float*
                                        uint64_t* my_nprobe_dev, float* t_recalls_dev, int flags,
                                        float* distances_dev, int64_t* labels_dev) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     QueryBatch qb;
     qb.n = (long)n;
     qb.x = x_dev;
@@ -517,6 +538,7 @@ int auncel_index_search_bounded(AuncelIndex* idx, int64_t n, const float* x, int
                                 const float* require_acc, const float* gt_kth, uint64_t* my_nprobe,
                                 float* t_recalls, int flags, float* distances, int64_t* labels) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     IvfIndex& ix = idx->ix;
     CUDA_CHECK(cudaSetDevice(ix.device));
     AUNCEL_CHECK(max_topk >= 1 && max_topk <= MAX_K, "max_topk must be in [1, 128]");
@@ -614,6 +636,7 @@ int auncel_merge_tables(int metric, int64_t n, int64_t k, int64_t nshard, const 
 int auncel_index_copy_subset_to(const AuncelIndex* idx, AuncelIndex* other, int subset_type, int64_t a1,
                                 int64_t a2) {
     API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
     const IvfIndex& ix = idx->ix;
     IvfIndex& ox = other->ix;
     AUNCEL_CHECK(ix.nlist == ox.nlist && ix.d == ox.d, "incompatible indexes");

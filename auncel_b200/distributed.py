@@ -53,17 +53,19 @@ class ReplicaGroup:
         n = len(x)
         base, D, I = self.search(x, k)
         per = (n + self.world - 1) // self.world
-        Dp = torch.full((per, k), np.nan, dtype=torch.float32)
-        Ip = torch.full((per, k), -1, dtype=torch.int64)
-        Dp[:len(D)] = torch.from_numpy(D)
-        Ip[:len(I)] = torch.from_numpy(I)
         if self.world == 1:
             return D, I
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.dist.get_backend(self.group) == "nccl" \
+            else torch.device("cpu")
+        Dp = torch.full((per, k), np.nan, dtype=torch.float32, device=dev)
+        Ip = torch.full((per, k), -1, dtype=torch.int64, device=dev)
+        Dp[:len(D)] = torch.from_numpy(D).to(dev)
+        Ip[:len(I)] = torch.from_numpy(I).to(dev)
         Dall = [torch.empty_like(Dp) for _ in range(self.world)]
         Iall = [torch.empty_like(Ip) for _ in range(self.world)]
         self.dist.all_gather(Dall, Dp, group=self.group)
         self.dist.all_gather(Iall, Ip, group=self.group)
-        return torch.cat(Dall)[:n].numpy(), torch.cat(Iall)[:n].numpy()
+        return torch.cat(Dall)[:n].cpu().numpy(), torch.cat(Iall)[:n].cpu().numpy()
 
 
 class ShardGroup:
