@@ -48,6 +48,7 @@ SYMBOLS = {
                                                      C.c_int, C.c_void_p, C.c_void_p]),
     "auncel_index_get_stats": (C.c_int, [_h, _d]),
     "auncel_index_set_pool_budget": (C.c_int, [_h, C.c_size_t]),
+    "auncel_index_set_option": (C.c_int, [_h, C.c_char_p, C.c_int]),
     "auncel_merge_tables": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, _f, _l, _l, _f, _l]),
     "auncel_merge_tables_device": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -581,6 +581,9 @@ int auncel_index_get_stats(const AuncelIndex* idx, double* out8) {
     out8[9] = (double)st.launches;
     out8[10] = (double)st.scan_launches;
     out8[11] = st.coarse_ms;
+    out8[12] = (double)st.tc_rounds;
+    out8[13] = (double)st.tc_candidates;
+    out8[14] = (double)st.tc_fallbacks;
     out8[0] = (double)st.nq;
     out8[1] = (double)st.nlist;
     out8[2] = (double)st.ndis;
@@ -590,6 +593,15 @@ int auncel_index_get_stats(const AuncelIndex* idx, double* out8) {
     out8[6] = (double)st.scan_pairs;
     out8[7] = (double)st.err_bits;
     return 0;
+}
+
+int auncel_index_set_option(AuncelIndex* idx, const char* name, int value) {
+    API_TRY
+    std::string n(name ? name : "");
+    if (n == "tensor_core_filter") idx->ix.tc_mode = value;      // 0 off, 1 auto, 2 whenever heaps are full
+    else if (n == "exact_ties") idx->ix.exact_ties = value != 0;  // replay the reference's heap order
+    else AUNCEL_THROW(-2, "unknown option " + n);
+    API_CATCH
 }
 
 int auncel_index_set_pool_budget(AuncelIndex* idx, size_t bytes) {

@@ -70,6 +70,7 @@ struct SearchStats {  // IndexIVFStats, IndexIVF.h:361-374
     uint64_t nq = 0, nlist = 0, ndis = 0, nheap_updates = 0;
     double quantization_ms = 0, search_ms = 0;
     uint64_t rounds = 0, scan_tiles = 0, scan_pairs = 0, launches = 0, scan_launches = 0;
+    uint64_t tc_rounds = 0, tc_candidates = 0, tc_fallbacks = 0;
     double coarse_ms = 0;
     double scan_ms = 0;      // device time of the scan kernels of the last search
     uint64_t err_bits = 0;   // ERR_* bits raised by the last search
@@ -138,6 +139,9 @@ struct IvfIndex {
     DevBuf<int> list_cnt, list_pair_off, list_tile_off, list_cursor;
     DevBuf<unsigned long long> pairs;
     DevBuf<float> q_sorted;
+    DevBuf<float> vnorm, qnorm;              // squared norms of arena rows / of the batch's queries
+    DevBuf<unsigned long long> tc_cand;      // survivors of the tensor-core filter
+    int tc_mode = 1;                         // 0 off, 1 automatic, 2 whenever every active heap is full
     DevBuf<int> ctl;           // small control block (counters)
     PinnedBuf<int> h_ctl;
     DevBuf<float> io_f;        // host-API staging

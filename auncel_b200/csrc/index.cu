@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "merge.cuh"
+#include "tcfilter.cuh"
 
 namespace auncel {
 
@@ -238,6 +239,8 @@ void IvfIndex::add_device(long n, const float* x_dev, const long long* ids_host,
     std::swap(ids.cap, nids.cap);
     h_list_off = new_off;
     make_codes_tensor_map(codes_tmap, codes.p, new_total, dpad);
+    launch_row_norms(codes.p, new_total, dpad, vnorm.ensure(std::max<size_t>(new_total, 1)), stream);
+    CUDA_CHECK(cudaStreamSynchronize(stream));
     ntotal += n;  // the reference counts skipped (-1) vectors too, IndexIVFFlat.cpp:79
 }
 
@@ -361,6 +364,7 @@ void IvfIndex::search(const QueryBatch& qb) {
         xs = q_x.p;
     }
     coarse_rank(n, xs);
+    if (tc_mode) launch_row_norms(xs, n, dpad, qnorm.ensure(n), stream);
     CUDA_CHECK(cudaEventRecord(ev2, stream));
     CUDA_CHECK(cudaMemsetAsync(ctl.p, 0, (CTL_SIZE + 8) * sizeof(int), stream));
     uint64_t launches = 2 * ((n + 65535L * 64 - 1) / (65535L * 64)) + (dpad != d ? 1 : 0) + 2 /*init, finalize*/ +
@@ -417,6 +421,7 @@ void IvfIndex::search(const QueryBatch& qb) {
 
     // ---- rounds
     int n_active = h_list_off[nlist] > 0 ? (int)n : 0;  // an empty index has nothing to scan
+    int min_rcnt = 0;
     int r0 = 0;
     int* act_cur = active.p;
     int* act_nxt = active2.p;
@@ -449,6 +454,19 @@ void IvfIndex::search(const QueryBatch& qb) {
         while (S > 1 && (size_t)n_active * w * S * nsub * K > pool_entries) S--;
         rp.qt = nsub == 4 ? 8 : SCAN_QT;
         rp.nsub = nsub;
+        rp.unsorted = 0;
+        // tensor-core filter round: every remaining query already holds K results, so only a
+        // handful of vectors per list can still enter -- filter with TF32 MMAs, rerank exactly
+        const bool all_full = stats.rounds > 0 && min_rcnt >= K;
+        bool use_tc = tc_mode == 2 ? all_full : (tc_mode == 1 && all_full && avg_q >= 24.0 && r0 >= 2);
+        if (use_tc && getenv("AUNCEL_NO_TC")) use_tc = false;
+        const int Ntc = tc_tile_queries(dpad);
+        if (use_tc) {
+            S = 1;
+            rp.qt = Ntc;
+            rp.nsub = nsub = 1;
+            rp.unsorted = 1;
+        }
         rp.active = act_cur;
         rp.n_active = n_active;
         rp.r0 = r0;
@@ -460,9 +478,9 @@ void IvfIndex::search(const QueryBatch& qb) {
         rp.cand_off = reinterpret_cast<unsigned*>(pool.p + slots * K * 4);
         rp.slot_cnt = slot_cnt.ensure(slots);
         rp.pairs = pairs.ensure((size_t)n_active * w);
-        rp.xq_sorted = q_sorted.ensure(((size_t)n_active * w + SCAN_QT) * dpad);
+        rp.xq_sorted = q_sorted.ensure(((size_t)n_active * w + 256) * dpad);
         alignas(64) unsigned char qmap[128];
-        make_queries_tensor_map(qmap, rp.xq_sorted, (long long)n_active * w + SCAN_QT, dpad);
+        make_queries_tensor_map(qmap, rp.xq_sorted, (long long)n_active * w + 256, dpad);
 
         if (scan_ev.size() < 2 * (stats.rounds + 1)) {
             cudaEvent_t a, b;
@@ -476,13 +494,45 @@ void IvfIndex::search(const QueryBatch& qb) {
                             ctl.p + CTL_NFIX, c_dis.p, c_keys.p, stream);
         launch_plan(rp, stream);
         CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds], stream));
-        launch_scan(rp, codes_tmap, qmap, num_sms, stream);
+        bool scanned = false;
+        if (use_tc) {
+            TcArgs ta;
+            ta.vnorm = vnorm.p;
+            ta.qnorm = qnorm.p;
+            ta.c1 = 2.f * (1.02f / 512.f + (float)dpad / 2097152.f);
+            ta.c2 = 1.f / 1048576.f;
+            ta.c3 = 1.f / 16384.f;
+            ta.cand_cap = (int)std::min<size_t>((size_t)64 << 20, std::max<size_t>((size_t)n_active * w * 8, 1 << 16));
+            ta.cand = tc_cand.ensure(ta.cand_cap);
+            ta.N = Ntc;
+            alignas(64) unsigned char bmap[128];
+            make_queries_tensor_map_tc(bmap, rp.xq_sorted, (long long)n_active * w + 256, dpad, Ntc);
+            CUDA_CHECK(cudaMemsetAsync(ctl.p + CTL_NCAND, 0, 2 * sizeof(int), stream));  // NCAND, OVERFLOW
+            launch_tc_filter(rp, ta, codes_tmap, bmap, num_sms, stream);
+            launch_rerank(rp, ta, num_sms, stream);
+            CUDA_CHECK(cudaMemcpyAsync(h_ctl.p, ctl.p, CTL_SIZE * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaStreamSynchronize(stream));
+            launches += 2;
+            stats.tc_candidates += (uint64_t)h_ctl.p[CTL_NCAND];
+            if (h_ctl.p[CTL_OVERFLOW]) {
+                // more survivors than a slot / the list can hold: redo the round with the exact scan
+                stats.tc_fallbacks++;
+                rp.qt = SCAN_QT;
+                rp.unsorted = 0;
+                launch_plan(rp, stream);
+            } else {
+                stats.tc_rounds++;
+                scanned = true;
+            }
+        }
+        if (!scanned) launch_scan(rp, codes_tmap, qmap, num_sms, stream);
         CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds + 1], stream));
         launch_merge_check(rp, tp, stream);
         launches += 7 + (exact_ties ? 2 : 0);  // [collect_ties, heap_order,] plan x3, gather, scan, merge_check, compact_active
         launch_compact_active(rp, r0 + (int)w, act_nxt, h_ctl.p, stream);
         CUDA_CHECK(cudaStreamSynchronize(stream));
         n_active = h_ctl.p[CTL_N_ACTIVE];
+        min_rcnt = h_ctl.p[CTL_MIN_RCNT];
         if (debug_rounds)
             round_log.push_back({r0, (int)w, (int)S, rp.n_active, h_ctl.p[CTL_TOTAL_TILES], h_ctl.p[CTL_TOTAL_PAIRS]});
         stats.rounds++;

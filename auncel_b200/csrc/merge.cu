@@ -154,8 +154,43 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
         const int nseg = rp.S * rp.nsub;
         for (int seg = 0; seg < nseg; seg++) {
             const long slot = ((long)a * rp.w + p_rel) * nseg + seg;
-            const int c = rp.slot_cnt[slot];
+            const int c = min(rp.slot_cnt[slot], K);
             if (c == 0) continue;
+            if (rp.unsorted) {
+                // tensor-core rounds: rerank_kernel appended survivors in arrival order; order them
+                // by (distance, offset) like the scan kernel does, in place
+                for (int i = lane; i < KP; i += 32) {
+                    unsigned long long kk = ~0ull;
+                    if (i < c) {
+                        uint32_t o = f2ord(rp.cand_d[slot * K + i]);
+                        if (metric == METRIC_IP) o = ~o;
+                        kk = ((unsigned long long)o << 32) | rp.cand_off[slot * K + i];
+                    }
+                    sm.key[i] = kk;
+                }
+                __syncwarp();
+                for (int size = 2; size <= KP; size <<= 1)
+                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                        for (int t = lane; t < KP / 2; t += 32) {
+                            int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                            bool up = ((lo & size) == 0);
+                            unsigned long long x = sm.key[lo], y = sm.key[hi];
+                            if ((x > y) == up) {
+                                sm.key[lo] = y;
+                                sm.key[hi] = x;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                for (int i = lane; i < c; i += 32) {
+                    unsigned long long kk = sm.key[i];
+                    uint32_t o = (uint32_t)(kk >> 32);
+                    if (metric == METRIC_IP) o = ~o;
+                    rp.cand_d[slot * K + i] = ord2f(o);
+                    rp.cand_off[slot * K + i] = (unsigned)(kk & 0xffffffffu);
+                }
+                __syncwarp();
+            }
             for (int i = lane; i < KP; i += 32) {
                 unsigned long long k1 = ~0ull, k2 = ~0ull;
                 if (i < rcnt) {
@@ -302,12 +337,14 @@ __global__ void compact_active_kernel(RoundParams rp, int r1, int* active_out) {
     if (rp.st.bound[q] > r1) {
         int pos = atomicAdd(&rp.ctl[CTL_N_ACTIVE], 1);
         active_out[pos] = q;
+        atomicMin(&rp.ctl[CTL_MIN_RCNT], rp.st.rcnt[q]);  // are all remaining queries' heaps full?
     }
 }
 
 void launch_compact_active(const RoundParams& rp, int r1, int* active_out, int* h_ctl_pinned,
                            cudaStream_t s) {
     CUDA_CHECK(cudaMemsetAsync(rp.ctl + CTL_N_ACTIVE, 0, sizeof(int), s));
+    CUDA_CHECK(cudaMemsetAsync(rp.ctl + CTL_MIN_RCNT, 0x7f, sizeof(int), s));
     if (rp.n_active > 0) {
         compact_active_kernel<<<(unsigned)((rp.n_active + 255) / 256), 256, 0, s>>>(rp, r1, active_out);
         CUDA_CHECK(cudaGetLastError());

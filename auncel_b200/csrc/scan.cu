@@ -21,6 +21,7 @@
 
 #include "exact.cuh"
 #include "scan.cuh"
+#include "tcfilter.cuh"
 
 namespace auncel {
 
@@ -510,6 +511,10 @@ void make_codes_tensor_map(void* out_map, const float* codes, long long nrows, i
 
 void make_queries_tensor_map(void* out_map, const float* xq_sorted, long long nrows, int dpad) {
     make_tensor_map_2d(out_map, xq_sorted, nrows, dpad, SCAN_QT, false);
+}
+
+void make_queries_tensor_map_tc(void* out_map, const float* xq_sorted, long long nrows, int dpad, int N) {
+    make_tensor_map_2d(out_map, xq_sorted, nrows, dpad, N, true);
 }
 
 void launch_scan(const RoundParams& rp, const void* tmap, const void* qmap, int num_sms, cudaStream_t s) {

@@ -6,7 +6,7 @@ namespace auncel {
 
 // control block slots (device ints, mirrored to pinned host memory once per round)
 enum { CTL_N_ACTIVE = 0, CTL_TOTAL_TILES = 1, CTL_TILE_COUNTER = 2, CTL_TOTAL_PAIRS = 3,
-       CTL_ERR = 4, CTL_NFIX = 5, CTL_SIZE = 16 };
+       CTL_ERR = 4, CTL_NFIX = 5, CTL_NCAND = 6, CTL_OVERFLOW = 7, CTL_MIN_RCNT = 8, CTL_SIZE = 16 };
 
 // per-query running state, SoA, carved from IvfIndex::state
 struct QState {
@@ -61,6 +61,7 @@ struct RoundParams {
     int r0, w, S;
     int qt;               // queries per scan tile this round: 32 (wide) or 8 (narrow)
     int nsub;             // sub-slots per (query, rank, segment): 4 in narrow rounds, else 1
+    int unsorted;         // 1: slots were filled by rerank_kernel in arrival order (tensor-core rounds)
     // plan
     int* list_cnt;
     int* list_pair_off;   // nlist + 1

@@ -1,0 +1,390 @@
+// Tensor-core candidate filter for the bulk rounds of the scan (subsystem (2), large batches).
+//
+// When every query of a round already holds K results, almost no vector of a newly probed
+// list can enter its top-K: only those with distance < tau (IndexIVFFlat.cpp:129).  Instead of
+// evaluating all (query, vector) distances with the exact 3-op FP32 sequence, this kernel
+//   1. computes dot(q, v) for a whole (256-query x 128-vector) tile with tcgen05.mma
+//      kind::tf32 (operands are the same fp32 rows, staged by TMA with 128B swizzle, read by
+//      the tensor core with the low 13 mantissa bits ignored), accumulating in TMEM;
+//   2. turns it into a LOWER bound of the reference distance,
+//        ||q||^2 + ||v||^2 - 2 dot  -  E(q, v),   E = c1 ||q|| ||v|| + c2 (||q||^2+||v||^2) + c3 |tau|
+//      (c1 covers two tf32 truncations per product, 2 * 2^-10 relative, plus the accumulation;
+//      see DESIGN.md section 4) and keeps the pair only if the bound is below tau;
+//   3. emits the survivors (a few per query per round) to a global list; rerank_kernel
+//      recomputes them with the reference's exact arithmetic (exact.cuh) and applies the
+//      reference's strict test.  Results are therefore bit-identical to the SIMT path; the
+//      tensor cores only decide what is worth computing exactly.
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected lane),
+// warps 2-5 epilogue (TMEM -> registers -> filter).  TMEM: 2 x 256 fp32 columns, double
+// buffered so the MMAs of block b+1 overlap the filter of block b.
+#include <cuda.h>
+
+#include "exact.cuh"
+#include "scan.cuh"
+#include "tcfilter.cuh"
+
+namespace auncel {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_ASTAGES = 4;
+constexpr int TC_A_BYTES = 128 * 128;        // 128 rows x 32 f32
+constexpr int TC_B_MAX = 128 * 1024;         // resident query tile: nchunk x N x 128 B
+constexpr int TC_NMAX = 256;
+constexpr size_t TC_SMEM = 1024 + TC_B_MAX + (size_t)TC_ASTAGES * TC_A_BYTES + 2 * (TC_NMAX * 8 + 64);
+
+struct TileMeta {
+    int flags;  // 1 = no more tiles
+    int nblk;
+    int Qt;
+    int pair0;
+    long long row0;  // first arena row of the list
+    int L;           // list length
+    int pad;
+    float2 q[TC_NMAX];  // (c1 * ||q||, rhs) per query column
+};
+
+__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(unsigned long long* b, int c) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(c));
+}
+__device__ __forceinline__ void mb_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+}
+__device__ __forceinline__ void mb_wait(unsigned long long* b, unsigned parity) {
+    unsigned ok = 0;
+    const unsigned a = s32(b);
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok)
+                     : "r"(a), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(s32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(s32(bar))
+                 : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4,
+// LBO = 1 (unused for swizzled K-major), SBO = 1024 B between 8-row groups, version 1, layout 2.
+__device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
+    return (unsigned long long)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((unsigned long long)(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned idesc,
+                                          unsigned accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap amap,
+                 const __grid_constant__ CUtensorMap bmap) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) unsigned long long a_full[TC_ASTAGES], a_empty[TC_ASTAGES], b_full, b_empty, t_full[2],
+        t_empty[2], m_full[2], m_empty[2];
+    __shared__ unsigned tmem_base_s;
+    unsigned char* smem = smem_dyn + ((1024u - (s32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char* Bsm = smem;
+    unsigned char* Asm = smem + TC_B_MAX;
+    TileMeta* meta = reinterpret_cast<TileMeta*>(Asm + (size_t)TC_ASTAGES * TC_A_BYTES);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = ta.N, dpad = rp.dpad;
+    const int nchunk = (dpad + 31) / 32;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_ASTAGES; s++) {
+            mb_init(&a_full[s], 1);
+            mb_init(&a_empty[s], 1);
+        }
+        mb_init(&b_full, 1);
+        mb_init(&b_empty, 1);
+        for (int i = 0; i < 2; i++) {
+            mb_init(&t_full[i], 1);
+            mb_init(&t_empty[i], 4);
+            mb_init(&m_full[i], 1);
+            mb_init(&m_empty[i], 5);  // MMA warp + 4 epilogue warps
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {  // TMEM: 512 columns (2 accumulators of up to 256 columns)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s32(&tmem_base_s)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // =========================== producer ===========================
+        const int total_tiles = rp.ctl[CTL_TOTAL_TILES];
+        unsigned ita = 0;
+        for (unsigned t = 0;; t++) {
+            int T = 0;
+            if (lane == 0) T = atomicAdd(&rp.ctl[CTL_TILE_COUNTER], 1);
+            T = __shfl_sync(0xffffffffu, T, 0);
+            const int m = t & 1;
+            TileMeta* mt = &meta[m];
+            mb_wait(&m_empty[m], ((t >> 1) & 1) ^ 1);
+            if (T >= total_tiles) {
+                if (lane == 0) {
+                    mt->flags = 1;
+                    mb_arrive(&m_full[m]);
+                }
+                break;
+            }
+            int lo = 0, hi = (int)rp.nlist;
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (rp.list_tile_off[mid] <= T) lo = mid; else hi = mid;
+            }
+            const int l = lo;
+            const int cnt_l = rp.list_pair_off[l + 1] - rp.list_pair_off[l];
+            const int qt = T - rp.list_tile_off[l];  // S == 1 in tensor-core rounds
+            const long long L0 = rp.list_off[l];
+            const int L = (int)(rp.list_off[l + 1] - L0);
+            const int Qt = min(N, cnt_l - qt * N);
+            const int pair0 = rp.list_pair_off[l] + qt * N;
+            const int nblk = (L + 127) / 128;
+            for (int j = lane; j < N; j += 32) {
+                float2 c = make_float2(0.f, METRIC == METRIC_L2 ? -FLT_MAX : FLT_MAX);  // never passes
+                if (j < Qt) {
+                    unsigned long long pr = rp.pairs[pair0 + j];
+                    int q = rp.active[(int)(pr >> 32)];
+                    float tau = rp.st.tau[q], nq = ta.qnorm[q];
+                    if (METRIC == METRIC_L2) {
+                        // pass <=> nv(1-c2) - 2 dot - c1 |q||v|  <  tau + c3|tau| - nq(1-c2)
+                        c.x = ta.c1 * sqrtf(nq);
+                        c.y = tau + ta.c3 * fabsf(tau) - nq * (1.f - ta.c2);
+                    } else {
+                        // pass <=> dot + c1/2 |q||v|  >  tau - c3|tau|
+                        c.x = 0.5f * ta.c1 * sqrtf(nq);
+                        c.y = tau - ta.c3 * fabsf(tau);
+                    }
+                }
+                mt->q[j] = c;
+            }
+            if (lane == 0) {
+                mt->flags = 0;
+                mt->nblk = nblk;
+                mt->Qt = Qt;
+                mt->pair0 = pair0;
+                mt->row0 = L0;
+                mt->L = L;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mb_arrive(&m_full[m]);
+                // queries: resident for the whole tile, one swizzled [N x 32] block per k-chunk
+                mb_wait(&b_empty, (t & 1) ^ 1);
+                mb_expect_tx(&b_full, (unsigned)(nchunk * N * 128));
+                for (int c = 0; c < nchunk; c++) tma2d(Bsm + (size_t)c * N * 128, &bmap, c * 32, pair0, &b_full);
+                for (int blk = 0; blk < nblk; blk++)
+                    for (int c = 0; c < nchunk; c++, ita++) {
+                        const int s = ita % TC_ASTAGES;
+                        mb_wait(&a_empty[s], ((ita / TC_ASTAGES) & 1) ^ 1);
+                        mb_expect_tx(&a_full[s], TC_A_BYTES);
+                        tma2d(Asm + (size_t)s * TC_A_BYTES, &amap, c * 32, (int)(L0 + (long long)blk * 128), &a_full[s]);
+                    }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        // idesc: D = f32, A = B = tf32, both K-major, N >> 3, M = 128 >> 4
+        const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((128u >> 4) << 24);
+        unsigned ita = 0, blkc = 0;
+        for (unsigned t = 0;; t++) {
+            const int m = t & 1;
+            mb_wait(&m_full[m], (t >> 1) & 1);
+            const int flags = meta[m].flags, nblk = meta[m].nblk;
+            __syncwarp();
+            if (lane == 0) mb_arrive(&m_empty[m]);
+            if (flags) break;
+            mb_wait(&b_full, t & 1);
+            for (int blk = 0; blk < nblk; blk++, blkc++) {
+                const int buf = blkc & 1;
+                mb_wait(&t_empty[buf], ((blkc >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const unsigned d_tmem = tmem_base + buf * 256;
+                for (int c = 0; c < nchunk; c++, ita++) {
+                    const int s = ita % TC_ASTAGES;
+                    mb_wait(&a_full[s], (ita / TC_ASTAGES) & 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const unsigned a0 = s32(Asm + (size_t)s * TC_A_BYTES), b0 = s32(Bsm + (size_t)c * N * 128);
+#pragma unroll
+                        for (int k = 0; k < 4; k++)  // K = 8 tf32 = 32 bytes per instruction
+                            umma_tf32(d_tmem, umma_desc(a0 + k * 32), umma_desc(b0 + k * 32), idesc, (c | k) != 0);
+                        umma_commit(&a_empty[s]);  // frees the A stage when these MMAs have read it
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) umma_commit(&t_full[buf]);
+                __syncwarp();
+            }
+            if (lane == 0) umma_commit(&b_empty);  // the tile's MMAs are done with the query block
+            __syncwarp();
+        }
+    } else {
+        // =========================== epilogue ===========================
+        const int wq = warp & 3;  // TMEM lane quarter this warp may read
+        unsigned blkc = 0;
+        for (unsigned t = 0;; t++) {
+            const int m = t & 1;
+            mb_wait(&m_full[m], (t >> 1) & 1);
+            const TileMeta* mt = &meta[m];
+            if (mt->flags) {
+                __syncwarp();
+                if (lane == 0) mb_arrive(&m_empty[m]);
+                break;
+            }
+            const int nblk = mt->nblk, L = mt->L, pair0 = mt->pair0;
+            const long long row0 = mt->row0;
+            for (int blk = 0; blk < nblk; blk++, blkc++) {
+                const int buf = blkc & 1;
+                const int v = blk * 128 + wq * 32 + lane;
+                const bool valid = v < L;
+                const float nv = valid ? ta.vnorm[row0 + v] : 0.f;
+                const float snv = sqrtf(nv);
+                const float nvp = METRIC == METRIC_L2 ? nv * (1.f - ta.c2) : 0.f;
+                mb_wait(&t_full[buf], (blkc >> 1) & 1);
+                tc_fence_after();
+                for (int cg = 0; cg < N / 32; cg++) {
+                    unsigned r[32];
+                    tmem_ld32(tmem_base + ((unsigned)(wq * 32) << 16) + buf * 256 + cg * 32, r);
+                    unsigned hits = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float2 c = mt->q[cg * 32 + j];
+                        const float dot = __uint_as_float(r[j]);
+                        bool pass;
+                        if (METRIC == METRIC_L2)
+                            pass = __fmaf_rn(-c.x, snv, __fmaf_rn(-2.f, dot, nvp)) < c.y;
+                        else
+                            pass = __fmaf_rn(c.x, snv, dot) > c.y;
+                        hits |= (pass ? 1u : 0u) << j;
+                    }
+                    if (!valid) hits = 0;
+                    while (hits) {
+                        const int j = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const int pos = atomicAdd(&rp.ctl[CTL_NCAND], 1);
+                        if (pos < ta.cand_cap)
+                            ta.cand[pos] = ((unsigned long long)(unsigned)(pair0 + cg * 32 + j) << 32) | (unsigned)v;
+                        else
+                            rp.ctl[CTL_OVERFLOW] = 1;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mb_arrive(&t_empty[buf]);
+            }
+            __syncwarp();
+            if (lane == 0) mb_arrive(&m_empty[m]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+}
+
+// Survivors of the filter, recomputed with the reference's arithmetic and test.
+template <int METRIC>
+__global__ void rerank_kernel(RoundParams rp, TcArgs ta) {
+    const int ncand = min(rp.ctl[CTL_NCAND], ta.cand_cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += gridDim.x * blockDim.x) {
+        const unsigned long long c = ta.cand[i];
+        const int pos = (int)(c >> 32);
+        const unsigned v = (unsigned)(c & 0xffffffffu);
+        const unsigned long long pr = rp.pairs[pos];
+        const int a = (int)(pr >> 32), p_rel = (int)(pr & 0xffffffffu);
+        const int q = rp.active[a];
+        const int l = rp.ckeys[(long long)q * rp.nlist + rp.r0 + p_rel];
+        const float4* x = reinterpret_cast<const float4*>(rp.xq_sorted + (long long)pos * rp.dpad);
+        const float4* y = reinterpret_cast<const float4*>(rp.codes + (rp.list_off[l] + v) * (long long)rp.dpad);
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < rp.dpad / 4; k++) exact_step<METRIC>(s, x[k], y[k]);
+        const float dist = exact_finish(s);
+        const float tau = rp.st.tau[q];
+        if (METRIC == METRIC_L2 ? dist < tau : dist > tau) {
+            const long slot = (long)a * rp.w + p_rel;  // S == nsub == 1
+            const int o = atomicAdd(&rp.slot_cnt[slot], 1);
+            if (o < rp.K) {
+                rp.cand_d[slot * rp.K + o] = dist;
+                rp.cand_off[slot * rp.K + o] = v;
+            } else {
+                rp.ctl[CTL_OVERFLOW] = 1;
+            }
+        }
+    }
+}
+
+// ||v||^2 of every arena row (double accumulation, rounded to float)
+__global__ void row_norms_kernel(const float* __restrict__ x, long long n, int dpad, float* __restrict__ out) {
+    long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    double s = 0.0;
+    for (int c = lane; c < dpad; c += 32) {
+        double v = x[r * dpad + c];
+        s += v * v;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[r] = (float)s;
+}
+
+void launch_row_norms(const float* x, long long n, int dpad, float* out, cudaStream_t s) {
+    if (n == 0) return;
+    row_norms_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(x, n, dpad, out);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+int tc_tile_queries(int dpad) {
+    int nchunk = (dpad + 31) / 32;
+    int n = TC_B_MAX / (nchunk * 128);
+    n = std::min(n, TC_NMAX) / 32 * 32;  // the epilogue reads TMEM 32 columns at a time
+    return n;
+}
+
+void launch_tc_filter(const RoundParams& rp, const TcArgs& ta, const void* amap, const void* bmap, int num_sms,
+                      cudaStream_t s) {
+    auto kern = rp.metric == METRIC_L2 ? tc_filter_kernel<METRIC_L2> : tc_filter_kernel<METRIC_IP>;
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    kern<<<num_sms, TC_THREADS, TC_SMEM, s>>>(rp, ta, *reinterpret_cast<const CUtensorMap*>(amap),
+                                             *reinterpret_cast<const CUtensorMap*>(bmap));
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_rerank(const RoundParams& rp, const TcArgs& ta, int num_sms, cudaStream_t s) {
+    auto kern = rp.metric == METRIC_L2 ? rerank_kernel<METRIC_L2> : rerank_kernel<METRIC_IP>;
+    kern<<<num_sms * 8, 128, 0, s>>>(rp, ta);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace auncel

@@ -1,0 +1,23 @@
+#pragma once
+#include "scan.cuh"
+
+namespace auncel {
+
+struct TcArgs {
+    const float* vnorm;   // ||v||^2 per arena row
+    const float* qnorm;   // ||q||^2 per query of the batch
+    float c1, c2, c3;     // error-bound constants, see tcfilter.cu
+    unsigned long long* cand;  // survivors: (pair position << 32) | offset in list
+    int cand_cap;
+    int N;                // queries per tile (multiple of 32, <= 256)
+};
+
+int tc_tile_queries(int dpad);
+void launch_row_norms(const float* x, long long n, int dpad, float* out, cudaStream_t s);
+void launch_tc_filter(const RoundParams& rp, const TcArgs& ta, const void* codes_map, const void* queries_map,
+                      int num_sms, cudaStream_t s);
+void launch_rerank(const RoundParams& rp, const TcArgs& ta, int num_sms, cudaStream_t s);
+// tensor map over xq_sorted with an N-row, 128B-swizzled box (the MMA's B operand)
+void make_queries_tensor_map_tc(void* out_map, const float* xq_sorted, long long nrows, int dpad, int N);
+
+}  // namespace auncel

@@ -117,3 +117,27 @@ def test_small_pool_budget_same_answer(case):
     ix.set_pool_budget(1 << 30)
     assert np.array_equal(mynp, g["b2_my_nprobe"])
     assert np.array_equal(D, g["b2_D"])
+
+
+@pytest.mark.parametrize("pi", [0, 2])
+def test_bounded_search_tensor_core_filter(case, pi):
+    """Rounds served by the tcgen05 TF32 filter + exact rerank give the same bits."""
+    c, g, xb, q, ix = case
+    ts, ses = int(g["ts"]), int(g["ses"])
+    mult, stdm, eb = PARAMS[pi]
+    ix.set_error_model(golden_traces(g), mult, stdm)
+    ix.set_option("tensor_core_filter", 2)
+    try:
+        D, I, mynp = ix.search_bounded(q[ts:], c["k"], c["qk"], g[f"b{pi}_acc"][ts:])
+        st = ix.stats()
+        assert st["tc_rounds"] > 0 and st["tc_fallbacks"] == 0, st
+        assert np.array_equal(mynp, g[f"b{pi}_my_nprobe"])
+        assert np.array_equal(D, g[f"b{pi}_D"])
+        assert_results_match(D, I, g[f"b{pi}_D"], g[f"b{pi}_I"], what="tc bounded")
+        ix.nprobe = 16
+        D, I = ix.search(q, c["k"])
+        assert ix.stats()["tc_rounds"] > 0
+        assert np.array_equal(D, g["fixed_D_16"])
+        assert_results_match(D, I, g["fixed_D_16"], g["fixed_I_16"], what="tc fixed")
+    finally:
+        ix.set_option("tensor_core_filter", 1)
