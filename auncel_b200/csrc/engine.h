@@ -141,6 +141,7 @@ struct IvfIndex {
     DevBuf<float> q_sorted;
     DevBuf<float> vnorm, qnorm;              // squared norms of arena rows / of the batch's queries
     DevBuf<unsigned long long> tc_cand;      // survivors of the tensor-core filter
+    DevBuf<int> pair_flag;                   // per slot: overflowed in a tensor-core round
     int tc_mode = 1;                         // 0 off, 1 automatic, 2 whenever every active heap is full
     DevBuf<int> ctl;           // small control block (counters)
     PinnedBuf<int> h_ctl;

@@ -421,7 +421,7 @@ void IvfIndex::search(const QueryBatch& qb) {
 
     // ---- rounds
     int n_active = h_list_off[nlist] > 0 ? (int)n : 0;  // an empty index has nothing to scan
-    int min_rcnt = 0;
+    int min_rcnt = 0, not_full = (int)n;
     int r0 = 0;
     int* act_cur = active.p;
     int* act_nxt = active2.p;
@@ -455,10 +455,15 @@ void IvfIndex::search(const QueryBatch& qb) {
         rp.qt = nsub == 4 ? 8 : SCAN_QT;
         rp.nsub = nsub;
         rp.unsorted = 0;
-        // tensor-core filter round: every remaining query already holds K results, so only a
-        // handful of vectors per list can still enter -- filter with TF32 MMAs, rerank exactly
-        const bool all_full = stats.rounds > 0 && min_rcnt >= K;
-        bool use_tc = tc_mode == 2 ? all_full : (tc_mode == 1 && all_full && avg_q >= 24.0 && r0 >= 2);
+        rp.filtered = 0;
+        rp.pair_flag = nullptr;
+        // tensor-core filter round: (nearly) every remaining query already holds K results, so only
+        // a handful of vectors per list can still enter -- filter with TF32 MMAs, rerank exactly.
+        // The few queries whose heaps are not full yet let everything through and are redone by
+        // the exact scan (per-pair overflow), so they only cost time, never correctness.
+        const bool mostly_full = stats.rounds > 0 && (long)not_full * 50 <= (long)n_active;
+        bool use_tc = tc_mode == 2 ? (stats.rounds > 0 && min_rcnt >= K)
+                                   : (tc_mode == 1 && mostly_full && r0 >= 2 && avg_q >= 4.0 && (long)n_active * w >= 2048);
         if (use_tc && getenv("AUNCEL_NO_TC")) use_tc = false;
         const int Ntc = tc_tile_queries(dpad);
         if (use_tc) {
@@ -502,20 +507,22 @@ void IvfIndex::search(const QueryBatch& qb) {
             ta.c1 = 2.f * (1.02f / 512.f + (float)dpad / 2097152.f);
             ta.c2 = 1.f / 1048576.f;
             ta.c3 = 1.f / 16384.f;
-            ta.cand_cap = (int)std::min<size_t>((size_t)64 << 20, std::max<size_t>((size_t)n_active * w * 8, 1 << 16));
+            ta.cand_cap = (int)std::min<size_t>((size_t)16 << 20, std::max<size_t>((size_t)n_active * w * 32, 1 << 20));
             ta.cand = tc_cand.ensure(ta.cand_cap);
             ta.N = Ntc;
             alignas(64) unsigned char bmap[128];
             make_queries_tensor_map_tc(bmap, rp.xq_sorted, (long long)n_active * w + 256, dpad, Ntc);
             CUDA_CHECK(cudaMemsetAsync(ctl.p + CTL_NCAND, 0, 2 * sizeof(int), stream));  // NCAND, OVERFLOW
+            rp.pair_flag = pair_flag.ensure((size_t)n_active * w);
+            CUDA_CHECK(cudaMemsetAsync(rp.pair_flag, 0, (size_t)n_active * w * sizeof(int), stream));
             launch_tc_filter(rp, ta, codes_tmap, bmap, num_sms, stream);
             launch_rerank(rp, ta, num_sms, stream);
             CUDA_CHECK(cudaMemcpyAsync(h_ctl.p, ctl.p, CTL_SIZE * sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_CHECK(cudaStreamSynchronize(stream));
             launches += 2;
             stats.tc_candidates += (uint64_t)h_ctl.p[CTL_NCAND];
-            if (h_ctl.p[CTL_OVERFLOW]) {
-                // more survivors than a slot / the list can hold: redo the round with the exact scan
+            if (h_ctl.p[CTL_OVERFLOW] < 0) {
+                // the survivor list itself overflowed: redo the whole round with the exact scan
                 stats.tc_fallbacks++;
                 rp.qt = SCAN_QT;
                 rp.unsorted = 0;
@@ -523,6 +530,17 @@ void IvfIndex::search(const QueryBatch& qb) {
             } else {
                 stats.tc_rounds++;
                 scanned = true;
+                if (h_ctl.p[CTL_OVERFLOW] > 0) {
+                    // some (query, list) pairs had more than K survivors (loose or missing tau):
+                    // the exact scan redoes just those pairs and rewrites their slots
+                    stats.tc_fallbacks += 0;
+                    rp.qt = SCAN_QT;
+                    rp.filtered = 1;
+                    launch_plan(rp, stream);
+                    launch_scan(rp, codes_tmap, qmap, num_sms, stream);
+                    rp.filtered = 0;
+                    launches += 5;
+                }
             }
         }
         if (!scanned) launch_scan(rp, codes_tmap, qmap, num_sms, stream);
@@ -533,8 +551,10 @@ void IvfIndex::search(const QueryBatch& qb) {
         CUDA_CHECK(cudaStreamSynchronize(stream));
         n_active = h_ctl.p[CTL_N_ACTIVE];
         min_rcnt = h_ctl.p[CTL_MIN_RCNT];
+        not_full = h_ctl.p[CTL_NOT_FULL];
         if (debug_rounds)
-            round_log.push_back({r0, (int)w, (int)S, rp.n_active, h_ctl.p[CTL_TOTAL_TILES], h_ctl.p[CTL_TOTAL_PAIRS]});
+            round_log.push_back({r0, (int)w, rp.unsorted ? -1 : (int)(S * nsub), rp.n_active, h_ctl.p[CTL_TOTAL_TILES],
+                                 h_ctl.p[CTL_TOTAL_PAIRS]});
         stats.rounds++;
         stats.scan_tiles += (uint64_t)h_ctl.p[CTL_TOTAL_TILES];
         stats.scan_pairs += (uint64_t)h_ctl.p[CTL_TOTAL_PAIRS];

@@ -337,7 +337,8 @@ __global__ void compact_active_kernel(RoundParams rp, int r1, int* active_out) {
     if (rp.st.bound[q] > r1) {
         int pos = atomicAdd(&rp.ctl[CTL_N_ACTIVE], 1);
         active_out[pos] = q;
-        atomicMin(&rp.ctl[CTL_MIN_RCNT], rp.st.rcnt[q]);  // are all remaining queries' heaps full?
+        atomicMin(&rp.ctl[CTL_MIN_RCNT], rp.st.rcnt[q]);
+        if (rp.st.rcnt[q] < rp.K) atomicAdd(&rp.ctl[CTL_NOT_FULL], 1);  // heaps still holding neutral slots
     }
 }
 
@@ -345,6 +346,7 @@ void launch_compact_active(const RoundParams& rp, int r1, int* active_out, int* 
                            cudaStream_t s) {
     CUDA_CHECK(cudaMemsetAsync(rp.ctl + CTL_N_ACTIVE, 0, sizeof(int), s));
     CUDA_CHECK(cudaMemsetAsync(rp.ctl + CTL_MIN_RCNT, 0x7f, sizeof(int), s));
+    CUDA_CHECK(cudaMemsetAsync(rp.ctl + CTL_NOT_FULL, 0, sizeof(int), s));
     if (rp.n_active > 0) {
         compact_active_kernel<<<(unsigned)((rp.n_active + 255) / 256), 256, 0, s>>>(rp, r1, active_out);
         CUDA_CHECK(cudaGetLastError());

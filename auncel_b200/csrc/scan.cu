@@ -36,6 +36,7 @@ __global__ void plan_count_kernel(RoundParams rp) {
     if (p >= rp.st.bound[q]) return;
     int l = rp.ckeys[(long)q * rp.nlist + p];
     if (rp.list_off[l + 1] == rp.list_off[l]) return;  // IndexIVF.cpp:452-455
+    if (rp.filtered && !rp.pair_flag[idx]) return;     // (tensor-core rounds: slot index == idx)
     atomicAdd(&rp.list_cnt[l], 1);
 }
 
@@ -91,6 +92,10 @@ __global__ void plan_fill_kernel(RoundParams rp) {
     if (p >= rp.st.bound[q]) return;
     int l = rp.ckeys[(long)q * rp.nlist + p];
     if (rp.list_off[l + 1] == rp.list_off[l]) return;
+    if (rp.filtered) {
+        if (!rp.pair_flag[idx]) return;
+        rp.slot_cnt[idx] = 0;  // the exact scan rewrites this slot
+    }
     int pos = rp.list_pair_off[l] + atomicAdd(&rp.list_cursor[l], 1);
     rp.pairs[pos] = ((unsigned long long)(unsigned)a << 32) | (unsigned)p_rel;
 }
@@ -110,7 +115,7 @@ __global__ void gather_queries_kernel(RoundParams rp) {
 void launch_plan(const RoundParams& rp, cudaStream_t s) {
     long tot = (long)rp.n_active * rp.w;
     CUDA_CHECK(cudaMemsetAsync(rp.list_cnt, 0, rp.nlist * sizeof(int), s));
-    CUDA_CHECK(cudaMemsetAsync(rp.slot_cnt, 0, (size_t)tot * rp.S * rp.nsub * sizeof(int), s));
+    if (!rp.filtered) CUDA_CHECK(cudaMemsetAsync(rp.slot_cnt, 0, (size_t)tot * rp.S * rp.nsub * sizeof(int), s));
     unsigned blocks = (unsigned)((tot + 255) / 256);
     plan_count_kernel<<<blocks, 256, 0, s>>>(rp);
     plan_offsets_kernel<<<1, 1024, 0, s>>>(rp);

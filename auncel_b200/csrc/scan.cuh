@@ -6,7 +6,7 @@ namespace auncel {
 
 // control block slots (device ints, mirrored to pinned host memory once per round)
 enum { CTL_N_ACTIVE = 0, CTL_TOTAL_TILES = 1, CTL_TILE_COUNTER = 2, CTL_TOTAL_PAIRS = 3,
-       CTL_ERR = 4, CTL_NFIX = 5, CTL_NCAND = 6, CTL_OVERFLOW = 7, CTL_MIN_RCNT = 8, CTL_SIZE = 16 };
+       CTL_ERR = 4, CTL_NFIX = 5, CTL_NCAND = 6, CTL_OVERFLOW = 7, CTL_MIN_RCNT = 8, CTL_NOT_FULL = 9, CTL_SIZE = 16 };
 
 // per-query running state, SoA, carved from IvfIndex::state
 struct QState {
@@ -62,6 +62,8 @@ struct RoundParams {
     int qt;               // queries per scan tile this round: 32 (wide) or 8 (narrow)
     int nsub;             // sub-slots per (query, rank, segment): 4 in narrow rounds, else 1
     int unsorted;         // 1: slots were filled by rerank_kernel in arrival order (tensor-core rounds)
+    int* pair_flag;       // tensor-core rounds: per slot, 1 = overflowed -> redo this pair with the exact scan
+    int filtered;         // plan only the flagged pairs
     // plan
     int* list_cnt;
     int* list_pair_off;   // nlist + 1
@@ -77,7 +79,7 @@ struct RoundParams {
     QState st;
 };
 
-void launch_plan(const RoundParams& rp, cudaStream_t s);
+void launch_plan(const RoundParams& rp, cudaStream_t s);  // rp.filtered: only flagged pairs, slot counts kept
 void launch_scan(const RoundParams& rp, const void* codes_map, const void* queries_map, int num_sms, cudaStream_t s);
 void make_queries_tensor_map(void* out_map, const float* xq_sorted, long long nrows, int dpad);
 // CUtensorMap (128 B, 64 B aligned) over the list arena [nrows x dpad] f32, box 128 rows x 32 floats

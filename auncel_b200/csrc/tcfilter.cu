@@ -217,12 +217,14 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         // idesc: D = f32, A = B = tf32, both K-major, N >> 3, M = 128 >> 4
-        const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((128u >> 4) << 24);
+        const unsigned idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
         unsigned ita = 0, blkc = 0;
         for (unsigned t = 0;; t++) {
             const int m = t & 1;
             mb_wait(&m_full[m], (t >> 1) & 1);
             const int flags = meta[m].flags, nblk = meta[m].nblk;
+            const int Nt = min(N, (meta[m].Qt + 31) / 32 * 32);  // MMA N: only the columns that hold queries
+            const unsigned idesc = idesc0 | ((unsigned)(Nt >> 3) << 17);
             __syncwarp();
             if (lane == 0) mb_arrive(&m_empty[m]);
             if (flags) break;
@@ -265,6 +267,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                 break;
             }
             const int nblk = mt->nblk, L = mt->L, pair0 = mt->pair0;
+            const int ncg = min(N, (mt->Qt + 31) / 32 * 32) / 32;
             const long long row0 = mt->row0;
             for (int blk = 0; blk < nblk; blk++, blkc++) {
                 const int buf = blkc & 1;
@@ -275,7 +278,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                 const float nvp = METRIC == METRIC_L2 ? nv * (1.f - ta.c2) : 0.f;
                 mb_wait(&t_full[buf], (blkc >> 1) & 1);
                 tc_fence_after();
-                for (int cg = 0; cg < N / 32; cg++) {
+                for (int cg = 0; cg < ncg; cg++) {
                     unsigned r[32];
                     tmem_ld32(tmem_base + ((unsigned)(wq * 32) << 16) + buf * 256 + cg * 32, r);
                     unsigned hits = 0;
@@ -298,7 +301,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                         if (pos < ta.cand_cap)
                             ta.cand[pos] = ((unsigned long long)(unsigned)(pair0 + cg * 32 + j) << 32) | (unsigned)v;
                         else
-                            rp.ctl[CTL_OVERFLOW] = 1;
+                            rp.ctl[CTL_OVERFLOW] = -(1 << 30);  // survivor list full: the whole round is redone
                     }
                 }
                 tc_fence_before();
@@ -339,7 +342,8 @@ __global__ void rerank_kernel(RoundParams rp, TcArgs ta) {
                 rp.cand_d[slot * rp.K + o] = dist;
                 rp.cand_off[slot * rp.K + o] = v;
             } else {
-                rp.ctl[CTL_OVERFLOW] = 1;
+                rp.pair_flag[slot] = 1;  // more than K vectors of this list beat tau: exact scan redoes the pair
+                atomicAdd(&rp.ctl[CTL_OVERFLOW], 1);
             }
         }
     }
