@@ -414,7 +414,7 @@ int auncel_index_coarse_search(AuncelIndex* idx, int64_t n, const float* x, int6
     }
     ix.coarse_rank((long)n, xs);
     if (ix.exact_ties)
-        launch_fix_ties(ix.metric, ix.c_raw.p, ix.nlist, (int)nprobe, nullptr, (int)n, ix.c_tie0.p, (int)nprobe,
+        launch_fix_ties(ix.metric, ix.c_raw.p, ix.nlist, (int)nprobe, ix.entry_table((int)nprobe), nullptr, (int)n, ix.c_tie0.p, (int)nprobe,
                         nullptr, ix.fix_list.p, ix.ctl.p + 5, ix.c_dis.p, ix.c_keys.p, ix.stream);
     idx->D.ensure((size_t)n * nprobe);
     idx->I.ensure((size_t)n * nprobe);

@@ -6,6 +6,8 @@
 //   rank_rows_kernel   : full ranking of all nlist centroids per query (heap_reorder output of
 //                        IndexFlat::search with k = nprobe = nlist, profile.cpp:218-222)
 //   the same tile kernel also fills interdis_cem (IVF_pro.cpp:21-39) and does add()'s k=1 assign.
+#include <vector>
+
 #include "engine.h"
 #include "exact.cuh"
 
@@ -205,10 +207,34 @@ __device__ __forceinline__ bool ngt(unsigned long long a, unsigned long long b) 
     return (uint32_t)(a >> 32) > (uint32_t)(b >> 32);
 }
 
-// Heap.h:88-117 on a 1-based array
-__device__ __forceinline__ void heap_pop_dev(int k, unsigned long long* h) {
+// Heap.h:88-117 on a 1-based array, started at node `i` (1 = the literal algorithm).  Two tree
+// levels are resolved per shared-memory round trip: children and grandchildren are loaded
+// together, then the reference's decisions are applied in order -- same moves, half the
+// dependent latency.
+__device__ __forceinline__ void heap_pop_dev(int k, unsigned long long* h, int i = 1) {
     const unsigned long long v = h[k];
-    int i = 1;
+    while (4 * i + 3 <= k) {
+        const unsigned long long c1 = h[2 * i], c2 = h[2 * i + 1];
+        const ulonglong2 ga = *reinterpret_cast<const ulonglong2*>(&h[4 * i]);      // children of 2i
+        const ulonglong2 gb = *reinterpret_cast<const ulonglong2*>(&h[4 * i + 2]);  // children of 2i+1
+        const bool left = ngt(c1, c2);
+        const unsigned long long c = left ? c1 : c2;
+        if (ngt(v, c)) {
+            h[i] = v;
+            return;
+        }
+        h[i] = c;
+        i = left ? 2 * i : 2 * i + 1;
+        const unsigned long long g1 = left ? ga.x : gb.x, g2 = left ? ga.y : gb.y;
+        const bool gleft = ngt(g1, g2);
+        const unsigned long long g = gleft ? g1 : g2;
+        if (ngt(v, g)) {
+            h[i] = v;
+            return;
+        }
+        h[i] = g;
+        i = gleft ? 2 * i : 2 * i + 1;
+    }
     while (true) {
         const int i1 = i << 1, i2 = i1 + 1;
         if (i1 > k) break;
@@ -235,34 +261,46 @@ __device__ __forceinline__ void heap_push_dev(int k, unsigned long long* h, unsi
     h[i] = v;
 }
 
+// While neutral (FLT_MAX) slots remain, heap_pop walks from the root through neutral nodes --
+// right child when both are neutral, the neutral one otherwise -- moving neutral onto neutral
+// until it meets real values.  That prefix does not depend on the data, only on how many
+// elements were inserted: `entry[j]` is the node where insertion j meets its first real
+// comparison (precomputed on the host, heap_entry_table), so the replay starts there.
 template <int METRIC>
 __global__ void __launch_bounds__(32)
-heap_order_kernel(const float* __restrict__ raw, long nlist, int k, const int* __restrict__ fix_list,
-                  const int* __restrict__ nfix, float* __restrict__ out_dis, int* __restrict__ out_keys,
-                  int* __restrict__ tie0) {
+heap_order_kernel(const float* __restrict__ raw, long nlist, int k, const int* __restrict__ entry,
+                  const int* __restrict__ fix_list, const int* __restrict__ nfix, float* __restrict__ out_dis,
+                  int* __restrict__ out_keys, int* __restrict__ tie0) {
     if ((int)blockIdx.x >= *nfix) return;
-    extern __shared__ unsigned long long hp[];  // k nodes, used 1-based through h = hp - 1
-    unsigned long long* h = hp - 1;
+    extern __shared__ __align__(16) unsigned long long hp[];  // hp[0] unused: 1-based heap, 16 B aligned pairs
+    unsigned long long* h = hp;
     const long q = fix_list[blockIdx.x];
     const int lane = threadIdx.x;
     const float neut = METRIC == METRIC_L2 ? FLT_MAX : -FLT_MAX;
     uint32_t on = f2ord(neut);
     if (METRIC == METRIC_IP) on = ~on;
-    for (int i = lane; i < k; i += 32) hp[i] = ((unsigned long long)on << 32) | 0xffffffffu;  // heapify, id -1
+    for (int i = lane; i <= k; i += 32) hp[i] = ((unsigned long long)on << 32) | 0xffffffffu;  // heapify, id -1
     __syncwarp();
     if (lane == 0) {
         const float* row = raw + q * nlist;
         constexpr int PF = 8;  // software prefetch of the distance row
         float buf[PF];
+        int ebuf[PF];
 #pragma unroll
-        for (int t = 0; t < PF; t++) buf[t] = t < nlist ? __ldg(row + t) : 0.f;
+        for (int t = 0; t < PF; t++) {
+            buf[t] = t < nlist ? __ldg(row + t) : 0.f;
+            ebuf[t] = t < k ? __ldg(entry + t) : 1;
+        }
         for (long j0 = 0; j0 < nlist; j0 += PF) {
             float cur[PF];
+            int ecur[PF];
 #pragma unroll
             for (int t = 0; t < PF; t++) {
                 cur[t] = buf[t];
+                ecur[t] = ebuf[t];
                 long nj = j0 + PF + t;
                 buf[t] = nj < nlist ? __ldg(row + nj) : 0.f;
+                ebuf[t] = nj < k ? __ldg(entry + nj) : 1;
             }
 #pragma unroll
             for (int t = 0; t < PF; t++) {
@@ -271,7 +309,7 @@ heap_order_kernel(const float* __restrict__ raw, long nlist, int k, const int* _
                 uint32_t o = f2ord(cur[t]);
                 if (METRIC == METRIC_IP) o = ~o;
                 if (o < (uint32_t)(h[1] >> 32)) {  // dis < simi[0] (L2) / ip > simi[0] (IP), utils.cpp:441,479
-                    heap_pop_dev(k, h);
+                    heap_pop_dev(k, h, j < k ? ecur[t] : 1);
                     heap_push_dev(k, h, ((unsigned long long)o << 32) | (unsigned)j);
                 }
             }
@@ -285,13 +323,41 @@ heap_order_kernel(const float* __restrict__ raw, long nlist, int k, const int* _
     }
     __syncwarp();
     for (int i = lane; i < k; i += 32) {
-        const unsigned long long node = hp[i];
+        const unsigned long long node = hp[i + 1];
         uint32_t o = (uint32_t)(node >> 32);
         if (METRIC == METRIC_IP) o = ~o;
         out_dis[q * nlist + i] = ord2f(o);
         out_keys[q * nlist + i] = (int)(uint32_t)(node & 0xffffffffu);
     }
     if (lane == 0) tie0[q] = 0x7fffffff;
+}
+
+// entry[j], j < k: see heap_order_kernel.  Pure structure: simulate heap_pop on occupancy bits.
+void heap_entry_table(int k, std::vector<int>& entry) {
+    entry.assign(k, 1);
+    std::vector<char> real(k + 2, 0);
+    for (int j = 0; j < k; j++) {
+        // insertion j pops with v = h[k] (neutral for j == 0, real afterwards), then pushes at slot k
+        int i = 1;
+        if (j == 0) {
+            entry[0] = 1;  // v is neutral: the literal walk only shuffles neutral values
+        } else {
+            while (true) {
+                int i1 = i << 1, i2 = i1 + 1;
+                if (i1 > k) break;  // leaf of the neutral region: v lands here
+                bool left;
+                if (i2 == k + 1) left = true;
+                else if (real[i1] && real[i2]) break;          // first data-dependent comparison
+                else left = !real[i1] && real[i2];             // cmp(h[i1], h[i2]): neutral beats real, tie -> right
+                int c = left ? i1 : i2;
+                if (real[c]) break;                             // single real child (slot k's stale copy)
+                i = c;
+            }
+            entry[j] = i;
+            real[i] = 1;  // the hole of this pop ends here: one more real node
+        }
+        real[k] = 1;      // push places d_j at slot k (and may sift up only through real parents)
+    }
 }
 
 // queries (from `list`, or all n when list == nullptr) whose first tie lies below `bound`
@@ -305,16 +371,17 @@ __global__ void collect_ties_kernel(const int* __restrict__ list, int n, const i
     if (tie0[q] < b) fix_list[atomicAdd(nfix, 1)] = q;
 }
 
-void launch_fix_ties(int metric, const float* raw, long nlist, int k, const int* list, int n, int* tie0, int bound,
-                     const int* qbound, int* fix_list, int* nfix, float* out_dis, int* out_keys, cudaStream_t s) {
+void launch_fix_ties(int metric, const float* raw, long nlist, int k, const int* entry, const int* list, int n,
+                     int* tie0, int bound, const int* qbound, int* fix_list, int* nfix, float* out_dis, int* out_keys,
+                     cudaStream_t s) {
     if (n == 0) return;
     CUDA_CHECK(cudaMemsetAsync(nfix, 0, sizeof(int), s));
     collect_ties_kernel<<<(n + 255) / 256, 256, 0, s>>>(list, n, tie0, bound, qbound, fix_list, nfix);
-    size_t smem = (size_t)k * 8;
+    size_t smem = (size_t)(k + 2) * 8;
     AUNCEL_CHECK(smem <= 220 * 1024, "nlist too large for the exact tie replay");
     auto kern = metric == METRIC_L2 ? heap_order_kernel<METRIC_L2> : heap_order_kernel<METRIC_IP>;
     if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<n, 32, smem, s>>>(raw, nlist, k, fix_list, nfix, out_dis, out_keys, tie0);
+    kern<<<n, 32, smem, s>>>(raw, nlist, k, entry, fix_list, nfix, out_dis, out_keys, tie0);
     CUDA_CHECK(cudaGetLastError());
 }
 

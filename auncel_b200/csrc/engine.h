@@ -130,6 +130,9 @@ struct IvfIndex {
     DevBuf<int> c_keys;        // n x nlist ranked centroid ids
     DevBuf<int> c_tie0;        // n: first rank with an equal-distance neighbour (INT_MAX: none / replayed)
     DevBuf<int> fix_list;      // scratch for the tie replay
+    DevBuf<int> heap_entry;    // heap_entry_table(heap_entry_k), device copy
+    int heap_entry_k = -1;
+    const int* entry_table(int k);
     bool exact_ties = true;
     DevBuf<float> dtb;         // n x max_num
     DevBuf<unsigned char> state;  // per-query running state, see search.cu
@@ -194,8 +197,9 @@ void launch_rank_rows(int metric, const float* dis, long nq, long nlist, float* 
                       int* tie0, cudaStream_t s);
 // replay the reference's size-k heap for the queries of `list` (all n if null) that have equal
 // coarse distances below rank `bound`; rewrites their rows of out_dis/out_keys in heap order
-void launch_fix_ties(int metric, const float* raw, long nlist, int k, const int* list, int n, int* tie0, int bound,
-                     const int* qbound, int* fix_list, int* nfix, float* out_dis, int* out_keys, cudaStream_t s);
+void heap_entry_table(int k, std::vector<int>& entry);
+void launch_fix_ties(int metric, const float* raw, long nlist, int k, const int* entry, const int* list, int n,
+                     int* tie0, int bound, const int* qbound, int* fix_list, int* nfix, float* out_dis, int* out_keys, cudaStream_t s);
 void launch_interdis(int metric, const float* cent, long nlist, int dpad, float* out, cudaStream_t s);
 void launch_merge_tables(int metric, long n, long k, long nshard, const float* all_D,
                          const long long* all_I, const long long* translations, float* D,

@@ -297,6 +297,18 @@ void IvfIndex::set_error_model(int arcos_size, int ntr, const long* trace_off, c
     std_m = sm;
 }
 
+const int* IvfIndex::entry_table(int k) {
+    if (k != heap_entry_k) {
+        std::vector<int> e;
+        heap_entry_table(k, e);
+        heap_entry.ensure(k);
+        CUDA_CHECK(cudaMemcpyAsync(heap_entry.p, e.data(), k * sizeof(int), cudaMemcpyHostToDevice, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        heap_entry_k = k;
+    }
+    return heap_entry.p;
+}
+
 ErrModelView IvfIndex::model_view() const {
     ErrModelView m;
     m.arcos = d_arcos.p;
@@ -409,7 +421,7 @@ void IvfIndex::search(const QueryBatch& qb) {
     tp.snapshots = qb.snapshots;
     tp.n_traces = expected_traces();
     if (qb.mode != 0 && exact_ties)  // set_online reads ranks 0..max_num
-        launch_fix_ties(metric, c_raw.p, nlist, nprobe, nullptr, (int)n, c_tie0.p, tp.max_num + 1, nullptr, fix_list.p,
+        launch_fix_ties(metric, c_raw.p, nlist, nprobe, entry_table(nprobe), nullptr, (int)n, c_tie0.p, tp.max_num + 1, nullptr, fix_list.p,
                         ctl.p + CTL_NFIX, c_dis.p, c_keys.p, stream);
     if (qb.mode != 0) {
         float* dtb_p = qb.dtb_out ? qb.dtb_out : dtb.ensure((size_t)n * tp.max_num);
@@ -495,7 +507,7 @@ void IvfIndex::search(const QueryBatch& qb) {
             scan_ev.push_back(b);
         }
         if (exact_ties)  // ranks [r0, r0+w) are about to be scanned: their order must be the reference's
-            launch_fix_ties(metric, c_raw.p, nlist, nprobe, act_cur, n_active, c_tie0.p, r0 + (int)w, rp.st.bound, fix_list.p,
+            launch_fix_ties(metric, c_raw.p, nlist, nprobe, entry_table(nprobe), act_cur, n_active, c_tie0.p, r0 + (int)w, rp.st.bound, fix_list.p,
                             ctl.p + CTL_NFIX, c_dis.p, c_keys.p, stream);
         launch_plan(rp, stream);
         CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds], stream));
