@@ -584,6 +584,10 @@ int auncel_index_get_stats(const AuncelIndex* idx, double* out8) {
     out8[12] = (double)st.tc_rounds;
     out8[13] = (double)st.tc_candidates;
     out8[14] = (double)st.tc_fallbacks;
+    out8[15] = st.tc_ms;
+    out8[16] = (double)st.tc_ndis;
+    out8[17] = st.simt_ms;
+    out8[18] = (double)st.simt_ndis;
     out8[0] = (double)st.nq;
     out8[1] = (double)st.nlist;
     out8[2] = (double)st.ndis;

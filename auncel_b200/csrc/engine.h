@@ -71,6 +71,10 @@ struct SearchStats {  // IndexIVFStats, IndexIVF.h:361-374
     double quantization_ms = 0, search_ms = 0;
     uint64_t rounds = 0, scan_tiles = 0, scan_pairs = 0, launches = 0, scan_launches = 0;
     uint64_t tc_rounds = 0, tc_candidates = 0, tc_fallbacks = 0;
+    double tc_ms = 0;        // device time of the tensor-core filter kernels
+    uint64_t tc_ndis = 0;    // distance evaluations (sum of |list| over pairs) they covered
+    uint64_t simt_ndis = 0;  // ... covered by exact-scan rounds
+    double simt_ms = 0;      // device time of the scan phase of those rounds
     double coarse_ms = 0;
     double scan_ms = 0;      // device time of the scan kernels of the last search
     uint64_t err_bits = 0;   // ERR_* bits raised by the last search
@@ -157,6 +161,9 @@ struct IvfIndex {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     std::vector<cudaEvent_t> scan_ev;  // pairs of events around every scan launch
+    std::vector<cudaEvent_t> tc_ev;    // pairs of events around every tensor-core filter launch
+    DevBuf<unsigned long long> round_work;
+    PinnedBuf<unsigned long long> h_round_work;
     SearchStats stats;
     bool debug_rounds = false;
     std::vector<std::array<int, 6>> round_log;

@@ -43,6 +43,7 @@ IvfIndex::~IvfIndex() {
     if (ev1) cudaEventDestroy(ev1);
     if (ev2) cudaEventDestroy(ev2);
     for (auto e : scan_ev) cudaEventDestroy(e);
+    for (auto e : tc_ev) cudaEventDestroy(e);
 }
 
 void IvfIndex::set_centroids(const float* c, bool compute_interdis) {
@@ -398,6 +399,10 @@ void IvfIndex::search(const QueryBatch& qb) {
     rp.K = K;
     rp.st.carve(state.p, n, K);
     rp.ctl = ctl.p;
+    rp.round_work = round_work.ensure(1);
+    h_round_work.ensure(1);
+    std::vector<int> tc_round_of;     // per round: index of its tensor-core event pair, or -1
+    std::vector<uint64_t> round_ndis;
     rp.list_cnt = list_cnt.ensure(nlist);
     rp.list_pair_off = list_pair_off.ensure(nlist + 1);
     rp.list_tile_off = list_tile_off.ensure(nlist + 1);
@@ -509,9 +514,12 @@ void IvfIndex::search(const QueryBatch& qb) {
         if (exact_ties)  // ranks [r0, r0+w) are about to be scanned: their order must be the reference's
             launch_fix_ties(metric, c_raw.p, nlist, nprobe, entry_table(nprobe), act_cur, n_active, c_tie0.p, r0 + (int)w, rp.st.bound, fix_list.p,
                             ctl.p + CTL_NFIX, c_dis.p, c_keys.p, stream);
+        CUDA_CHECK(cudaMemsetAsync(rp.round_work, 0, sizeof(unsigned long long), stream));
         launch_plan(rp, stream);
+        CUDA_CHECK(cudaMemcpyAsync(h_round_work.p, rp.round_work, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds], stream));
         bool scanned = false;
+        int tc_idx = -1;
         if (use_tc) {
             TcArgs ta;
             ta.vnorm = vnorm.p;
@@ -527,7 +535,17 @@ void IvfIndex::search(const QueryBatch& qb) {
             CUDA_CHECK(cudaMemsetAsync(ctl.p + CTL_NCAND, 0, 2 * sizeof(int), stream));  // NCAND, OVERFLOW
             rp.pair_flag = pair_flag.ensure((size_t)n_active * w);
             CUDA_CHECK(cudaMemsetAsync(rp.pair_flag, 0, (size_t)n_active * w * sizeof(int), stream));
+            tc_idx = (int)stats.tc_rounds + (int)stats.tc_fallbacks;
+            if (tc_ev.size() < 2 * (size_t)(tc_idx + 1)) {
+                cudaEvent_t a, b;
+                CUDA_CHECK(cudaEventCreate(&a));
+                CUDA_CHECK(cudaEventCreate(&b));
+                tc_ev.push_back(a);
+                tc_ev.push_back(b);
+            }
+            CUDA_CHECK(cudaEventRecord(tc_ev[2 * tc_idx], stream));
             launch_tc_filter(rp, ta, codes_tmap, bmap, num_sms, stream);
+            CUDA_CHECK(cudaEventRecord(tc_ev[2 * tc_idx + 1], stream));
             launch_rerank(rp, ta, num_sms, stream);
             CUDA_CHECK(cudaMemcpyAsync(h_ctl.p, ctl.p, CTL_SIZE * sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -536,9 +554,13 @@ void IvfIndex::search(const QueryBatch& qb) {
             if (h_ctl.p[CTL_OVERFLOW] < 0) {
                 // the survivor list itself overflowed: redo the whole round with the exact scan
                 stats.tc_fallbacks++;
+                tc_idx = -1;
                 rp.qt = SCAN_QT;
                 rp.unsorted = 0;
+                rp.filtered = 0;
+                CUDA_CHECK(cudaMemsetAsync(rp.round_work, 0, sizeof(unsigned long long), stream));
                 launch_plan(rp, stream);
+                CUDA_CHECK(cudaMemcpyAsync(h_round_work.p, rp.round_work, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
             } else {
                 stats.tc_rounds++;
                 scanned = true;
@@ -561,6 +583,8 @@ void IvfIndex::search(const QueryBatch& qb) {
         launches += 7 + (exact_ties ? 2 : 0);  // [collect_ties, heap_order,] plan x3, gather, scan, merge_check, compact_active
         launch_compact_active(rp, r0 + (int)w, act_nxt, h_ctl.p, stream);
         CUDA_CHECK(cudaStreamSynchronize(stream));
+        tc_round_of.push_back(tc_idx);
+        round_ndis.push_back(h_round_work.p[0]);
         n_active = h_ctl.p[CTL_N_ACTIVE];
         min_rcnt = h_ctl.p[CTL_MIN_RCNT];
         not_full = h_ctl.p[CTL_NOT_FULL];
@@ -594,6 +618,15 @@ void IvfIndex::search(const QueryBatch& qb) {
         float t = 0.f;
         CUDA_CHECK(cudaEventElapsedTime(&t, scan_ev[2 * r], scan_ev[2 * r + 1]));
         scan_ms_total += t;
+        if (tc_round_of[r] >= 0) {
+            float tt = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&tt, tc_ev[2 * tc_round_of[r]], tc_ev[2 * tc_round_of[r] + 1]));
+            stats.tc_ms += tt;
+            stats.tc_ndis += round_ndis[r];
+        } else {
+            stats.simt_ms += t;
+            stats.simt_ndis += round_ndis[r];
+        }
         if (debug_rounds && r < round_log.size())
             fprintf(stderr, "[auncel] round %2d r0=%4d w=%4d S=%2d active=%6d tiles=%7d pairs=%8d scan=%8.3f ms\n", (int)r,
                     round_log[r][0], round_log[r][1], round_log[r][2], round_log[r][3], round_log[r][4],

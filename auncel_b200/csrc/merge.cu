@@ -159,37 +159,62 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
             if (rp.unsorted) {
                 // tensor-core rounds: rerank_kernel appended survivors in arrival order; order them
                 // by (distance, offset) like the scan kernel does, in place
-                for (int i = lane; i < KP; i += 32) {
+                if (c <= 32) {
                     unsigned long long kk = ~0ull;
-                    if (i < c) {
-                        uint32_t o = f2ord(rp.cand_d[slot * K + i]);
+                    if (lane < c) {
+                        uint32_t o = f2ord(rp.cand_d[slot * K + lane]);
                         if (metric == METRIC_IP) o = ~o;
-                        kk = ((unsigned long long)o << 32) | rp.cand_off[slot * K + i];
+                        kk = ((unsigned long long)o << 32) | rp.cand_off[slot * K + lane];
                     }
-                    sm.key[i] = kk;
-                }
-                __syncwarp();
-                for (int size = 2; size <= KP; size <<= 1)
-                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                        for (int t = lane; t < KP / 2; t += 32) {
-                            int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-                            bool up = ((lo & size) == 0);
-                            unsigned long long x = sm.key[lo], y = sm.key[hi];
-                            if ((x > y) == up) {
-                                sm.key[lo] = y;
-                                sm.key[hi] = x;
-                            }
+#pragma unroll
+                    for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+                        for (int j = k2 >> 1; j > 0; j >>= 1) {
+                            unsigned long long other = __shfl_xor_sync(0xffffffffu, kk, j);
+                            bool up = ((lane & k2) == 0), lower = ((lane & j) == 0);
+                            unsigned long long mn = kk < other ? kk : other, mx = kk < other ? other : kk;
+                            kk = (lower == up) ? mn : mx;
                         }
-                        __syncwarp();
+                    if (lane < c) {
+                        uint32_t o = (uint32_t)(kk >> 32);
+                        if (metric == METRIC_IP) o = ~o;
+                        rp.cand_d[slot * K + lane] = ord2f(o);
+                        rp.cand_off[slot * K + lane] = (unsigned)(kk & 0xffffffffu);
                     }
-                for (int i = lane; i < c; i += 32) {
-                    unsigned long long kk = sm.key[i];
-                    uint32_t o = (uint32_t)(kk >> 32);
-                    if (metric == METRIC_IP) o = ~o;
-                    rp.cand_d[slot * K + i] = ord2f(o);
-                    rp.cand_off[slot * K + i] = (unsigned)(kk & 0xffffffffu);
+                    __syncwarp();
+                } else {
+                    for (int i = lane; i < KP; i += 32) {
+                        unsigned long long kk = ~0ull;
+                        if (i < c) {
+                            uint32_t o = f2ord(rp.cand_d[slot * K + i]);
+                            if (metric == METRIC_IP) o = ~o;
+                            kk = ((unsigned long long)o << 32) | rp.cand_off[slot * K + i];
+                        }
+                        sm.key[i] = kk;
+                    }
+                    __syncwarp();
+                    for (int size = 2; size <= KP; size <<= 1)
+                        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                            for (int t = lane; t < KP / 2; t += 32) {
+                                int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                                bool up = ((lo & size) == 0);
+                                unsigned long long x = sm.key[lo], y = sm.key[hi];
+                                if ((x > y) == up) {
+                                    sm.key[lo] = y;
+                                    sm.key[hi] = x;
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    for (int i = lane; i < c; i += 32) {
+                        unsigned long long kk = sm.key[i];
+                        uint32_t o = (uint32_t)(kk >> 32);
+                        if (metric == METRIC_IP) o = ~o;
+                        rp.cand_d[slot * K + i] = ord2f(o);
+                        rp.cand_off[slot * K + i] = (unsigned)(kk & 0xffffffffu);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             for (int i = lane; i < KP; i += 32) {
                 unsigned long long k1 = ~0ull, k2 = ~0ull;

@@ -29,15 +29,22 @@ namespace auncel {
 __global__ void plan_count_kernel(RoundParams rp) {
     long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
     long tot = (long)rp.n_active * rp.w;
-    if (idx >= tot) return;
-    int a = (int)(idx / rp.w), p_rel = (int)(idx - (long)a * rp.w);
-    int q = rp.active[a];
-    int p = rp.r0 + p_rel;
-    if (p >= rp.st.bound[q]) return;
-    int l = rp.ckeys[(long)q * rp.nlist + p];
-    if (rp.list_off[l + 1] == rp.list_off[l]) return;  // IndexIVF.cpp:452-455
-    if (rp.filtered && !rp.pair_flag[idx]) return;     // (tensor-core rounds: slot index == idx)
-    atomicAdd(&rp.list_cnt[l], 1);
+    unsigned long long work = 0;
+    if (idx < tot) {
+        int a = (int)(idx / rp.w), p_rel = (int)(idx - (long)a * rp.w);
+        int q = rp.active[a];
+        int p = rp.r0 + p_rel;
+        if (p < rp.st.bound[q]) {
+            int l = rp.ckeys[(long)q * rp.nlist + p];
+            long long sz = rp.list_off[l + 1] - rp.list_off[l];
+            if (sz > 0 && !(rp.filtered && !rp.pair_flag[idx])) {  // IndexIVF.cpp:452-455; filtered: slot == idx
+                atomicAdd(&rp.list_cnt[l], 1);
+                if (!rp.filtered) work = (unsigned long long)sz;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) work += __shfl_xor_sync(0xffffffffu, work, o);
+    if ((threadIdx.x & 31) == 0 && work) atomicAdd(rp.round_work, work);
 }
 
 // single block: exclusive scans over the lists

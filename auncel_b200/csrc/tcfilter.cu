@@ -14,8 +14,9 @@
 //      recomputes them with the reference's exact arithmetic (exact.cuh) and applies the
 //      reference's strict test.  Results are therefore bit-identical to the SIMT path; the
 //      tensor cores only decide what is worth computing exactly.
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected lane),
-// warps 2-5 epilogue (TMEM -> registers -> filter).  TMEM: 2 x 256 fp32 columns, double
+// Warp roles (224 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected lane),
+// warps 2-5 epilogue (TMEM -> registers -> filter), warp 6 tile scheduler (claims and decodes
+// the next tile and its per-query constants while the current one streams).  TMEM: 2 x 256 fp32 columns, double
 // buffered so the MMAs of block b+1 overlap the filter of block b.
 #include <cuda.h>
 
@@ -25,8 +26,8 @@
 
 namespace auncel {
 
-constexpr int TC_THREADS = 192;
-constexpr int TC_ASTAGES = 4;
+constexpr int TC_THREADS = 224;   // + warp 6: tile scheduler (decodes tiles one ahead of the TMA warp)
+constexpr int TC_ASTAGES = 5;
 constexpr int TC_A_BYTES = 128 * 128;        // 128 rows x 32 f32
 constexpr int TC_B_MAX = 128 * 1024;         // resident query tile: nchunk x N x 128 B
 constexpr int TC_NMAX = 256;
@@ -127,7 +128,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
             mb_init(&t_full[i], 1);
             mb_init(&t_empty[i], 4);
             mb_init(&m_full[i], 1);
-            mb_init(&m_empty[i], 5);  // MMA warp + 4 epilogue warps
+            mb_init(&m_empty[i], 6);  // TMA warp + MMA warp + 4 epilogue warps
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -140,16 +141,53 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
     tc_fence_after();
     const unsigned tmem_base = tmem_base_s;
 
-    if (warp == 0) {
-        // =========================== producer ===========================
+    if (warp == 6) {
+        // =========================== tile scheduler ===========================
         const int total_tiles = rp.ctl[CTL_TOTAL_TILES];
-        unsigned ita = 0;
         for (unsigned t = 0;; t++) {
             int T = 0;
             if (lane == 0) T = atomicAdd(&rp.ctl[CTL_TILE_COUNTER], 1);
             T = __shfl_sync(0xffffffffu, T, 0);
             const int m = t & 1;
             TileMeta* mt = &meta[m];
+            int l = 0, cnt_l = 0, qt = 0, L = 0, Qt = 0, pair0 = 0, nblk = 0;
+            long long L0 = 0;
+            float2 cq[TC_NMAX / 32];
+            if (T < total_tiles) {  // decode and gather the constants BEFORE waiting for the meta slot
+                int lo = 0, hi = (int)rp.nlist;
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (rp.list_tile_off[mid] <= T) lo = mid; else hi = mid;
+                }
+                l = lo;
+                cnt_l = rp.list_pair_off[l + 1] - rp.list_pair_off[l];
+                qt = T - rp.list_tile_off[l];  // S == 1 in tensor-core rounds
+                L0 = rp.list_off[l];
+                L = (int)(rp.list_off[l + 1] - L0);
+                Qt = min(N, cnt_l - qt * N);
+                pair0 = rp.list_pair_off[l] + qt * N;
+                nblk = (L + 127) / 128;
+#pragma unroll
+                for (int jj = 0; jj < TC_NMAX / 32; jj++) {
+                    const int j = jj * 32 + lane;
+                    float2 c = make_float2(0.f, METRIC == METRIC_L2 ? -FLT_MAX : FLT_MAX);  // never passes
+                    if (j < Qt) {
+                        unsigned long long pr = rp.pairs[pair0 + j];
+                        int q = rp.active[(int)(pr >> 32)];
+                        float tau = rp.st.tau[q], nq = ta.qnorm[q];
+                        if (METRIC == METRIC_L2) {
+                            // pass <=> nv(1-c2) - 2 dot - c1 |q||v|  <  tau + c3|tau| - nq(1-c2)
+                            c.x = ta.c1 * sqrtf(nq);
+                            c.y = tau + ta.c3 * fabsf(tau) - nq * (1.f - ta.c2);
+                        } else {
+                            // pass <=> dot + c1/2 |q||v|  >  tau - c3|tau|
+                            c.x = 0.5f * ta.c1 * sqrtf(nq);
+                            c.y = tau - ta.c3 * fabsf(tau);
+                        }
+                    }
+                    cq[jj] = c;
+                }
+            }
             mb_wait(&m_empty[m], ((t >> 1) & 1) ^ 1);
             if (T >= total_tiles) {
                 if (lane == 0) {
@@ -158,37 +196,9 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                 }
                 break;
             }
-            int lo = 0, hi = (int)rp.nlist;
-            while (hi - lo > 1) {
-                int mid = (lo + hi) >> 1;
-                if (rp.list_tile_off[mid] <= T) lo = mid; else hi = mid;
-            }
-            const int l = lo;
-            const int cnt_l = rp.list_pair_off[l + 1] - rp.list_pair_off[l];
-            const int qt = T - rp.list_tile_off[l];  // S == 1 in tensor-core rounds
-            const long long L0 = rp.list_off[l];
-            const int L = (int)(rp.list_off[l + 1] - L0);
-            const int Qt = min(N, cnt_l - qt * N);
-            const int pair0 = rp.list_pair_off[l] + qt * N;
-            const int nblk = (L + 127) / 128;
-            for (int j = lane; j < N; j += 32) {
-                float2 c = make_float2(0.f, METRIC == METRIC_L2 ? -FLT_MAX : FLT_MAX);  // never passes
-                if (j < Qt) {
-                    unsigned long long pr = rp.pairs[pair0 + j];
-                    int q = rp.active[(int)(pr >> 32)];
-                    float tau = rp.st.tau[q], nq = ta.qnorm[q];
-                    if (METRIC == METRIC_L2) {
-                        // pass <=> nv(1-c2) - 2 dot - c1 |q||v|  <  tau + c3|tau| - nq(1-c2)
-                        c.x = ta.c1 * sqrtf(nq);
-                        c.y = tau + ta.c3 * fabsf(tau) - nq * (1.f - ta.c2);
-                    } else {
-                        // pass <=> dot + c1/2 |q||v|  >  tau - c3|tau|
-                        c.x = 0.5f * ta.c1 * sqrtf(nq);
-                        c.y = tau - ta.c3 * fabsf(tau);
-                    }
-                }
-                mt->q[j] = c;
-            }
+#pragma unroll
+            for (int jj = 0; jj < TC_NMAX / 32; jj++)
+                if (jj * 32 + lane < N) mt->q[jj * 32 + lane] = cq[jj];
             if (lane == 0) {
                 mt->flags = 0;
                 mt->nblk = nblk;
@@ -198,8 +208,20 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                 mt->L = L;
             }
             __syncwarp();
+            if (lane == 0) mb_arrive(&m_full[m]);
+        }
+    } else if (warp == 0) {
+        // =========================== TMA producer ===========================
+        unsigned ita = 0;
+        for (unsigned t = 0;; t++) {
+            const int m = t & 1;
+            mb_wait(&m_full[m], (t >> 1) & 1);
+            const int flags = meta[m].flags, nblk = meta[m].nblk, pair0 = meta[m].pair0;
+            const long long L0 = meta[m].row0;
+            __syncwarp();
+            if (lane == 0) mb_arrive(&m_empty[m]);
+            if (flags) break;
             if (lane == 0) {
-                mb_arrive(&m_full[m]);
                 // queries: resident for the whole tile, one swizzled [N x 32] block per k-chunk
                 mb_wait(&b_empty, (t & 1) ^ 1);
                 mb_expect_tx(&b_full, (unsigned)(nchunk * N * 128));
@@ -253,7 +275,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
             if (lane == 0) umma_commit(&b_empty);  // the tile's MMAs are done with the query block
             __syncwarp();
         }
-    } else {
+    } else if (warp >= 2 && warp <= 5) {
         // =========================== epilogue ===========================
         const int wq = warp & 3;  // TMEM lane quarter this warp may read
         unsigned blkc = 0;
