@@ -588,6 +588,10 @@ int auncel_index_get_stats(const AuncelIndex* idx, double* out8) {
     out8[16] = (double)st.tc_ndis;
     out8[17] = st.simt_ms;
     out8[18] = (double)st.simt_ndis;
+    out8[19] = (double)st.tc_uniq;
+    out8[20] = (double)st.tc_staged;
+    out8[21] = (double)st.simt_uniq;
+    out8[22] = (double)st.simt_staged;
     out8[0] = (double)st.nq;
     out8[1] = (double)st.nlist;
     out8[2] = (double)st.ndis;

@@ -74,6 +74,7 @@ struct SearchStats {  // IndexIVFStats, IndexIVF.h:361-374
     double tc_ms = 0;        // device time of the tensor-core filter kernels
     uint64_t tc_ndis = 0;    // distance evaluations (sum of |list| over pairs) they covered
     uint64_t simt_ndis = 0;  // ... covered by exact-scan rounds
+    uint64_t tc_uniq = 0, tc_staged = 0, simt_uniq = 0, simt_staged = 0;  // vectors: distinct lists touched / staged per tile
     double simt_ms = 0;      // device time of the scan phase of those rounds
     double coarse_ms = 0;
     double scan_ms = 0;      // device time of the scan kernels of the last search

@@ -399,8 +399,9 @@ void IvfIndex::search(const QueryBatch& qb) {
     rp.K = K;
     rp.st.carve(state.p, n, K);
     rp.ctl = ctl.p;
-    rp.round_work = round_work.ensure(1);
-    h_round_work.ensure(1);
+    rp.round_work = round_work.ensure(4);
+    h_round_work.ensure(4);
+    std::vector<uint64_t> round_uniq, round_staged;
     std::vector<int> tc_round_of;     // per round: index of its tensor-core event pair, or -1
     std::vector<uint64_t> round_ndis;
     rp.list_cnt = list_cnt.ensure(nlist);
@@ -514,9 +515,9 @@ void IvfIndex::search(const QueryBatch& qb) {
         if (exact_ties)  // ranks [r0, r0+w) are about to be scanned: their order must be the reference's
             launch_fix_ties(metric, c_raw.p, nlist, nprobe, entry_table(nprobe), act_cur, n_active, c_tie0.p, r0 + (int)w, rp.st.bound, fix_list.p,
                             ctl.p + CTL_NFIX, c_dis.p, c_keys.p, stream);
-        CUDA_CHECK(cudaMemsetAsync(rp.round_work, 0, sizeof(unsigned long long), stream));
+        CUDA_CHECK(cudaMemsetAsync(rp.round_work, 0, 4 * sizeof(unsigned long long), stream));
         launch_plan(rp, stream);
-        CUDA_CHECK(cudaMemcpyAsync(h_round_work.p, rp.round_work, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaMemcpyAsync(h_round_work.p, rp.round_work, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds], stream));
         bool scanned = false;
         int tc_idx = -1;
@@ -558,9 +559,9 @@ void IvfIndex::search(const QueryBatch& qb) {
                 rp.qt = SCAN_QT;
                 rp.unsorted = 0;
                 rp.filtered = 0;
-                CUDA_CHECK(cudaMemsetAsync(rp.round_work, 0, sizeof(unsigned long long), stream));
+                CUDA_CHECK(cudaMemsetAsync(rp.round_work, 0, 4 * sizeof(unsigned long long), stream));
                 launch_plan(rp, stream);
-                CUDA_CHECK(cudaMemcpyAsync(h_round_work.p, rp.round_work, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+                CUDA_CHECK(cudaMemcpyAsync(h_round_work.p, rp.round_work, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
             } else {
                 stats.tc_rounds++;
                 scanned = true;
@@ -585,6 +586,8 @@ void IvfIndex::search(const QueryBatch& qb) {
         CUDA_CHECK(cudaStreamSynchronize(stream));
         tc_round_of.push_back(tc_idx);
         round_ndis.push_back(h_round_work.p[0]);
+        round_uniq.push_back(h_round_work.p[1]);
+        round_staged.push_back(h_round_work.p[2]);
         n_active = h_ctl.p[CTL_N_ACTIVE];
         min_rcnt = h_ctl.p[CTL_MIN_RCNT];
         not_full = h_ctl.p[CTL_NOT_FULL];
@@ -623,9 +626,13 @@ void IvfIndex::search(const QueryBatch& qb) {
             CUDA_CHECK(cudaEventElapsedTime(&tt, tc_ev[2 * tc_round_of[r]], tc_ev[2 * tc_round_of[r] + 1]));
             stats.tc_ms += tt;
             stats.tc_ndis += round_ndis[r];
+            stats.tc_uniq += round_uniq[r];
+            stats.tc_staged += round_staged[r];
         } else {
             stats.simt_ms += t;
             stats.simt_ndis += round_ndis[r];
+            stats.simt_uniq += round_uniq[r];
+            stats.simt_staged += round_staged[r];
         }
         if (debug_rounds && r < round_log.size())
             fprintf(stderr, "[auncel] round %2d r0=%4d w=%4d S=%2d active=%6d tiles=%7d pairs=%8d scan=%8.3f ms\n", (int)r,

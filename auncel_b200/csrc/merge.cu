@@ -147,11 +147,22 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
 
     const float* dtb = tp.dtb ? tp.dtb + (long)q * tp.max_num : nullptr;
 
+    unsigned nzmask = 0;
     for (int p_rel = 0; p_rel < rp.w; p_rel++) {
         const int stage = rp.r0 + p_rel + 1;
         if (stage > bound) break;
         // ---- merge the candidates of probe rank stage-1 (all segments)
         const int nseg = rp.S * rp.nsub;
+        if (nseg == 1) {
+            // 32 slot counts per coalesced load; a decided query has nothing to do at a stage
+            // without candidates (the tune block cannot change its state any more, :615-632)
+            if ((p_rel & 31) == 0) {
+                const int pl = p_rel + lane;
+                const int cv = pl < rp.w ? rp.slot_cnt[(long)a * rp.w + pl] : 0;
+                nzmask = __ballot_sync(0xffffffffu, cv > 0);
+            }
+            if (!((nzmask >> (p_rel & 31)) & 1u) && decided && stage < bound) continue;
+        }
         for (int seg = 0; seg < nseg; seg++) {
             const long slot = ((long)a * rp.w + p_rel) * nseg + seg;
             const int c = min(rp.slot_cnt[slot], K);

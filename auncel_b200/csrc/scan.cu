@@ -72,6 +72,13 @@ __global__ void __launch_bounds__(1024) plan_offsets_kernel(RoundParams rp) {
             rp.list_pair_off[l] = carry_pair + s_pair[threadIdx.x] - c;
             rp.list_tile_off[l] = carry_tile + s_tile[threadIdx.x] - t;
             rp.list_cursor[l] = 0;
+            if (c > 0 && !rp.filtered) {
+                // vectors of the lists this round touches (compulsory traffic) and vectors staged
+                // into shared memory (one pass per query tile)
+                unsigned long long L = (unsigned long long)(rp.list_off[l + 1] - rp.list_off[l]);
+                atomicAdd(rp.round_work + 1, L);
+                atomicAdd(rp.round_work + 2, L * (unsigned long long)((c + rp.qt - 1) / rp.qt));
+            }
         }
         __syncthreads();
         if (threadIdx.x == 1023) {

@@ -72,7 +72,8 @@ struct RoundParams {
     unsigned long long* pairs;
     float* xq_sorted;     // total_pairs x dpad: query rows in pair order
     int* ctl;
-    unsigned long long* round_work;  // sum of |list| over the round's pairs (algorithmic distance evaluations)
+    unsigned long long* round_work;  // [0] sum of |list| over the round's pairs (algorithmic distance evaluations),
+                                     // [1] vectors of the distinct lists touched, [2] vectors staged (one pass per query tile)
     // pool: slot = ((a * w + p_rel) * S + seg) * nsub + sub, K entries each
     float* cand_d;
     unsigned* cand_off;

@@ -195,11 +195,12 @@ class IndexIVFFlat:
             None if trec_t is None else trec_t.data_ptr(), flags, D_t.data_ptr(), I_t.data_ptr()))
 
     def stats(self):
-        out = (C.c_double * 20)()
+        out = (C.c_double * 24)()
         lib().auncel_index_get_stats(self.h, out)
         return dict(zip(["nq", "nlist", "ndis", "search_ms", "rounds", "scan_tiles", "scan_pairs", "err_bits",
                          "scan_ms", "launches", "scan_launches", "coarse_ms", "tc_rounds", "tc_candidates",
-                         "tc_fallbacks", "tc_ms", "tc_ndis", "simt_ms", "simt_ndis"], [float(v) for v in out]))
+                         "tc_fallbacks", "tc_ms", "tc_ndis", "simt_ms", "simt_ndis", "tc_uniq", "tc_staged",
+                         "simt_uniq", "simt_staged"], [float(v) for v in out]))
 
     def set_option(self, name, value):
         _ck(lib().auncel_index_set_option(self.h, name.encode(), int(value)))

@@ -130,9 +130,10 @@ int auncel_index_search_bounded_device(AuncelIndex* idx, int64_t n, const float*
  * scan launch) [9]=kernel launches [10]=scan-kernel launches [11]=coarse ms [12]=rounds served by
  * the tensor-core filter [13]=its survivors [14]=rounds it handed back to the exact scan
  * [15]=tensor-core filter kernel ms [16]=distance evaluations those launches covered
- * [17]=scan-phase ms of exact-scan rounds [18]=distance evaluations of those rounds.
- * out: 20 doubles */
-int auncel_index_get_stats(const AuncelIndex* idx, double* out20);
+ * [17]=scan-phase ms of exact-scan rounds [18]=distance evaluations of those rounds
+ * [19]/[21]=vectors of the distinct lists touched per launch, summed (tensor-core / exact rounds)
+ * [20]/[22]=vectors staged into shared memory (one list pass per query tile).  out: 24 doubles */
+int auncel_index_get_stats(const AuncelIndex* idx, double* out24);
 
 /* engine switches (results never change): "tensor_core_filter" 0 off / 1 automatic / 2 whenever
  * every active query holds K results; "exact_ties" 0/1 replay of the reference's heap order for
