@@ -426,9 +426,14 @@ void IvfIndex::search(const QueryBatch& qb) {
     tp.max_num = max_num();
     tp.snapshots = qb.snapshots;
     tp.n_traces = expected_traces();
-    if (qb.mode != 0 && exact_ties)  // set_online reads ranks 0..max_num
-        launch_fix_ties(metric, c_raw.p, nlist, nprobe, entry_table(nprobe), nullptr, (int)n, c_tie0.p, tp.max_num + 1, nullptr, fix_list.p,
-                        ctl.p + CTL_NFIX, c_dis.p, c_keys.p, stream);
+    // Small batches: one replay wave fits every tie-affected query, so fix all ranks up front
+    // instead of paying one wave per round.  Large batches: only what set_online reads
+    // (ranks 0..max_num) now, the rest lazily before each round.
+    const bool ties_all_upfront = exact_ties && n >= 16 && n <= 1024;
+    if (exact_ties && (qb.mode != 0 || ties_all_upfront))
+        launch_fix_ties(metric, c_raw.p, nlist, nprobe, entry_table(nprobe), nullptr, (int)n, c_tie0.p,
+                        ties_all_upfront ? nprobe : tp.max_num + 1, nullptr, fix_list.p, ctl.p + CTL_NFIX, c_dis.p,
+                        c_keys.p, stream);
     if (qb.mode != 0) {
         float* dtb_p = qb.dtb_out ? qb.dtb_out : dtb.ensure((size_t)n * tp.max_num);
         launch_set_online(metric, nlist, n, c_dis.p, c_keys.p, interdis.p, d_arcos.p, (int)h_arcos.size(), dtb_p,
@@ -454,7 +459,10 @@ void IvfIndex::search(const QueryBatch& qb) {
         w_cap = std::max(1L, std::min<long>(w_cap, 1024));
         long w = max_stage - r0;
         if (qb.mode == 1 && !qb.overhead_profile) {
-            w = std::min<long>(w, std::max(1, r0));
+            // few queries: start with a wider window -- speculative lists cost little HBM time,
+            // every extra round costs a fixed launch/sync latency
+            const long w0 = std::max(1L, std::min(32L, 4096L / n));
+            w = std::min<long>(w, std::max<long>(w0, r0));
         } else if ((long)n_active * max_stage >= 4096 && max_stage > 8) {
             // plain / calibration search: a few narrow rounds first, so that the bulk of the
             // lists is scanned against a tight threshold (cheap selection)
@@ -512,7 +520,7 @@ void IvfIndex::search(const QueryBatch& qb) {
             scan_ev.push_back(a);
             scan_ev.push_back(b);
         }
-        if (exact_ties)  // ranks [r0, r0+w) are about to be scanned: their order must be the reference's
+        if (exact_ties && !ties_all_upfront)  // ranks [r0, r0+w) are about to be scanned: their order must be the reference's
             launch_fix_ties(metric, c_raw.p, nlist, nprobe, entry_table(nprobe), act_cur, n_active, c_tie0.p, r0 + (int)w, rp.st.bound, fix_list.p,
                             ctl.p + CTL_NFIX, c_dis.p, c_keys.p, stream);
         CUDA_CHECK(cudaMemsetAsync(rp.round_work, 0, 4 * sizeof(unsigned long long), stream));
@@ -581,7 +589,7 @@ void IvfIndex::search(const QueryBatch& qb) {
         if (!scanned) launch_scan(rp, codes_tmap, qmap, num_sms, stream);
         CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds + 1], stream));
         launch_merge_check(rp, tp, stream);
-        launches += 7 + (exact_ties ? 2 : 0);  // [collect_ties, heap_order,] plan x3, gather, scan, merge_check, compact_active
+        launches += 7 + (exact_ties && !ties_all_upfront ? 2 : 0);  // [collect_ties, heap_order,] plan x3, gather, scan, merge_check, compact_active
         launch_compact_active(rp, r0 + (int)w, act_nxt, h_ctl.p, stream);
         CUDA_CHECK(cudaStreamSynchronize(stream));
         tc_round_of.push_back(tc_idx);
