@@ -158,7 +158,7 @@ struct IvfIndex {
     DevBuf<unsigned long long> io_u;
     DevBuf<unsigned long long> assign_best;
 
-    size_t pool_budget_bytes = (size_t)1 << 30;
+    size_t pool_budget_bytes = (size_t)4 << 30;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     std::vector<cudaEvent_t> scan_ev;  // pairs of events around every scan launch

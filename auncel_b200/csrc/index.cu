@@ -445,6 +445,7 @@ void IvfIndex::search(const QueryBatch& qb) {
     // ---- rounds
     int n_active = h_list_off[nlist] > 0 ? (int)n : 0;  // an empty index has nothing to scan
     int min_rcnt = 0, not_full = (int)n;
+    bool ties_done = false;
     int r0 = 0;
     int* act_cur = active.p;
     int* act_nxt = active2.p;
@@ -462,7 +463,13 @@ void IvfIndex::search(const QueryBatch& qb) {
             // few queries: start with a wider window -- speculative lists cost little HBM time,
             // every extra round costs a fixed launch/sync latency
             const long w0 = std::max(1L, std::min(32L, 4096L / n));
-            w = std::min<long>(w, std::max<long>(w0, r0));
+            // A query still undecided after r0 lists will stop no earlier than multipler * r0
+            // (my_nprobe = stage * multipler, IndexIVF.cpp:615-626), so growing the window by up to
+            // that factor scans nothing that would not be scanned anyway -- and every round saved is
+            // one pass over the arena saved.
+            double g = std::min<double>(std::max<double>(multipler, 2.0), 8.0);
+            if (const char* e = getenv("AUNCEL_GROWTH")) g = std::max(2.0, atof(e));
+            w = std::min<long>(w, std::max<long>(w0, (long)(r0 * (g - 1.0))));
         } else if ((long)n_active * max_stage >= 4096 && max_stage > 8) {
             // plain / calibration search: a few narrow rounds first, so that the bulk of the
             // lists is scanned against a tight threshold (cheap selection)
@@ -520,9 +527,15 @@ void IvfIndex::search(const QueryBatch& qb) {
             scan_ev.push_back(a);
             scan_ev.push_back(b);
         }
-        if (exact_ties && !ties_all_upfront)  // ranks [r0, r0+w) are about to be scanned: their order must be the reference's
-            launch_fix_ties(metric, c_raw.p, nlist, nprobe, entry_table(nprobe), act_cur, n_active, c_tie0.p, r0 + (int)w, rp.st.bound, fix_list.p,
-                            ctl.p + CTL_NFIX, c_dis.p, c_keys.p, stream);
+        if (exact_ties && !ties_all_upfront && !ties_done) {
+            // ranks [r0, r0+w) are about to be scanned: their order must be the reference's.  Once
+            // the remaining queries fit one replay wave, fix all of their ranks and stop checking.
+            const bool all_now = n_active <= 768;
+            launch_fix_ties(metric, c_raw.p, nlist, nprobe, entry_table(nprobe), act_cur, n_active, c_tie0.p,
+                            all_now ? nprobe : r0 + (int)w, rp.st.bound, fix_list.p, ctl.p + CTL_NFIX, c_dis.p,
+                            c_keys.p, stream);
+            ties_done = all_now;
+        }
         CUDA_CHECK(cudaMemsetAsync(rp.round_work, 0, 4 * sizeof(unsigned long long), stream));
         launch_plan(rp, stream);
         CUDA_CHECK(cudaMemcpyAsync(h_round_work.p, rp.round_work, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));

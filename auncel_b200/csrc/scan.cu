@@ -141,7 +141,7 @@ void launch_plan(const RoundParams& rp, cudaStream_t s) {
 // ------------------------------------------------------------------------- scan
 constexpr int NCONS = 8;                          // consumer warps
 constexpr int THREADS = (NCONS + 1) * 32;         // + 1 producer warp
-constexpr int STAGES = 4;
+constexpr int STAGES = 6;
 constexpr int QLD = SCAN_DK;                      // query row in smem, floats (dense TMA box)
 constexpr int VT_BYTES = SCAN_VT * SCAN_DK * 4;   // 16384: 128 rows x 128 B, 128B-swizzled by TMA
 constexpr int QT_BYTES = SCAN_QT * QLD * 4;       // 4096
