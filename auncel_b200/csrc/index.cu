@@ -446,6 +446,7 @@ void IvfIndex::search(const QueryBatch& qb) {
     int n_active = h_list_off[nlist] > 0 ? (int)n : 0;  // an empty index has nothing to scan
     int min_rcnt = 0, not_full = (int)n;
     bool ties_done = false;
+    const int tc_min_r0 = getenv("AUNCEL_TC_MIN_R0") ? atoi(getenv("AUNCEL_TC_MIN_R0")) : 2;
     int r0 = 0;
     int* act_cur = active.p;
     int* act_nxt = active2.p;
@@ -496,7 +497,7 @@ void IvfIndex::search(const QueryBatch& qb) {
         // the exact scan (per-pair overflow), so they only cost time, never correctness.
         const bool mostly_full = stats.rounds > 0 && (long)not_full * 50 <= (long)n_active;
         bool use_tc = tc_mode == 2 ? (stats.rounds > 0 && min_rcnt >= K)
-                                   : (tc_mode == 1 && mostly_full && r0 >= 2 && avg_q >= 4.0 && (long)n_active * w >= 2048);
+                                   : (tc_mode == 1 && mostly_full && r0 >= tc_min_r0 && avg_q >= 4.0 && (long)n_active * w >= 2048);
         if (use_tc && getenv("AUNCEL_NO_TC")) use_tc = false;
         const int Ntc = tc_tile_queries(dpad);
         if (use_tc) {
@@ -530,7 +531,7 @@ void IvfIndex::search(const QueryBatch& qb) {
         if (exact_ties && !ties_all_upfront && !ties_done) {
             // ranks [r0, r0+w) are about to be scanned: their order must be the reference's.  Once
             // the remaining queries fit one replay wave, fix all of their ranks and stop checking.
-            const bool all_now = n_active <= 768;
+            const bool all_now = n_active <= 1000;
             launch_fix_ties(metric, c_raw.p, nlist, nprobe, entry_table(nprobe), act_cur, n_active, c_tie0.p,
                             all_now ? nprobe : r0 + (int)w, rp.st.bound, fix_list.p, ctl.p + CTL_NFIX, c_dis.p,
                             c_keys.p, stream);

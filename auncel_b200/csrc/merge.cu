@@ -148,6 +148,11 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
     const float* dtb = tp.dtb ? tp.dtb + (long)q * tp.max_num : nullptr;
 
     unsigned nzmask = 0;
+    // cur_num (IVF_pro.cpp:258-291) reads only the first query_topk entries of the sorted heap, the
+    // boundary distances and the trace of `ind`: its value is reused until one of them changes
+    int cached_ind = -1, topq_dirty = 1;
+    unsigned cached_pre = 0;
+    const int qk_i = tp.query_topk;
     for (int p_rel = 0; p_rel < rp.w; p_rel++) {
         const int stage = rp.r0 + p_rel + 1;
         if (stage > bound) break;
@@ -167,6 +172,8 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
             const long slot = ((long)a * rp.w + p_rel) * nseg + seg;
             const int c = min(rp.slot_cnt[slot], K);
             if (c == 0) continue;
+            const int rcnt_before = rcnt;
+            const float kth_before = (qk_i >= 1 && rcnt >= qk_i) ? sm.Rd[qk_i - 1] : neut;
             if (rp.unsorted) {
                 // tensor-core rounds: rerank_kernel appended survivors in arrival order; order them
                 // by (distance, offset) like the scan kernel does, in place
@@ -272,6 +279,12 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
             }
             cur ^= 1;
             __syncwarp();
+            if (tp.mode == 1 && qk_i >= 1) {
+                // did a candidate enter the first query_topk positions?  (its best one must beat the
+                // old query_topk-th value; an equal value leaves the sorted values unchanged)
+                const float best = rp.cand_d[slot * K];
+                if (rcnt_before < qk_i || (metric == METRIC_L2 ? best < kth_before : best > kth_before)) topq_dirty = 1;
+            }
         }
 
         const bool cut_here = cut && stage == limit;  // max_codes break precedes both blocks (:541)
@@ -280,16 +293,22 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
         if (tp.mode == 1 && !tp.overhead_profile) {
             if (!decided) {
                 // ---- tune block, IndexIVF.cpp:551-626
-                const float* S = sm.Rd;
-                if (metric == METRIC_IP) {
-                    for (int i = lane; i < K; i += 32)
-                        sm.ang[i] = arcos_lookup(tp.model.arcos, tp.model.arcos_size, sm.Rd[i], &err);
-                    __syncwarp();
-                    S = sm.ang;
-                }
                 const int ind = stage_to_ind((size_t)stage, (size_t)rp.nlist);
                 const unsigned qk = (unsigned)tp.query_topk;
-                const unsigned pre = cur_num(tp.model, S, dtb, ind, qk, &err);
+                unsigned pre = cached_pre;
+                if (topq_dirty || ind != cached_ind) {
+                    const float* S = sm.Rd;
+                    if (metric == METRIC_IP) {
+                        for (int i = lane; i < K; i += 32)
+                            sm.ang[i] = arcos_lookup(tp.model.arcos, tp.model.arcos_size, sm.Rd[i], &err);
+                        __syncwarp();
+                        S = sm.ang;
+                    }
+                    pre = cur_num(tp.model, S, dtb, ind, qk, &err);
+                    cached_pre = pre;
+                    cached_ind = ind;
+                    topq_dirty = 0;
+                }
                 float recall = fdiv((float)pre, (float)qk);
                 const float ext = rcnt == K ? sm.Rd[K - 1] : neut;  // heap extreme (:573-587)
                 const float req = tp.require_acc[q];
