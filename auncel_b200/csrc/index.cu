@@ -483,10 +483,10 @@ void IvfIndex::search(const QueryBatch& qb) {
         S = std::max(1L, std::min<long>(S, 32));
         // narrow tiles (8 queries, rows split over warps) when lists are probed by few queries
         const double avg_q = (double)n_active * w / (double)std::min<long>(nlist, (long)n_active * w);
-        int nsub = avg_q <= 16.0 ? 4 : 1;
-        if ((size_t)n_active * w * nsub * K > pool_entries) nsub = 1;
+        int nsub = avg_q <= 10.0 ? 4 : avg_q <= 24.0 ? 2 : 1;
+        while (nsub > 1 && (size_t)n_active * w * nsub * K > pool_entries) nsub >>= 1;
         while (S > 1 && (size_t)n_active * w * S * nsub * K > pool_entries) S--;
-        rp.qt = nsub == 4 ? 8 : SCAN_QT;
+        rp.qt = SCAN_QT / nsub;
         rp.nsub = nsub;
         rp.unsorted = 0;
         rp.filtered = 0;

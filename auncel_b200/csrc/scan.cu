@@ -274,11 +274,12 @@ __device__ __forceinline__ void compact(unsigned long long* buf, int& cnt, float
     __syncwarp();
 }
 
-// NARROW = false: warp w owns queries 4w..4w+3 and all 128 rows of a block (4 per lane).
-// NARROW = true : tiles hold <= 8 queries; warp w owns queries 4(w/4)..+3 and rows 32(w%4)+lane
-//                 (1 per lane), so a list probed by few queries still keeps all warps busy; the
-//                 four row subsets of a query are written as four sub-slots.
-template <int METRIC, bool NARROW>
+// RSPLIT = 1: warp w owns queries 4w..4w+3 and all 128 rows of a block (4 per lane); 32 queries/tile.
+// RSPLIT = 2: 16 queries/tile; warp w owns queries 4(w/2)..+3 and 64 rows (2 per lane).
+// RSPLIT = 4: 8 queries/tile; warp w owns queries 4(w/4)..+3 and 32 rows (1 per lane).
+// Splitting the rows keeps all warps busy when a list is probed by few queries; the RSPLIT row
+// subsets of a query are written as RSPLIT sub-slots.
+template <int METRIC, int RSPLIT>
 __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap qmap) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES];
@@ -384,9 +385,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
     }
 
     // =========================== consumers ===========================
-    constexpr int TV = NARROW ? 1 : 4;                 // list rows per lane
-    const int qbase = NARROW ? (warp >> 2) * 4 : warp * 4;  // first query of this warp
-    const int rbase = NARROW ? (warp & 3) * 32 : 0;    // first row of this warp (rows rbase + lane + 32 j)
+    constexpr int TV = 4 / RSPLIT;                       // list rows per lane
+    const int qbase = (warp / RSPLIT) * 4;               // first query of this warp
+    const int rbase = (warp % RSPLIT) * (SCAN_VT / RSPLIT);  // first row of this warp (rows rbase + lane + 32 j)
     int cnt[4] = {0, 0, 0, 0};
     float tau[4] = {0.f, 0.f, 0.f, 0.f};
     float acc[4][TV][4];
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
             for (int i = 0; i < 4; i++) {
                 if (qbase + i < Qt && cnt[i] > 0) {
                     unsigned long long* buf = cand + (size_t)(warp * 4 + i) * CAP;
-                    const long sl = NARROW ? (long)slot[i] * 4 + (warp & 3) : (long)slot[i];
+                    const long sl = (long)slot[i] * RSPLIT + (warp % RSPLIT);
                     if (cnt[i] <= 32) {
                         unsigned long long key = lane < cnt[i] ? buf[lane] : ~0ull;
                         key = warp_sort_reg(key, lane);
@@ -537,8 +538,11 @@ void make_queries_tensor_map_tc(void* out_map, const float* xq_sorted, long long
 }
 
 void launch_scan(const RoundParams& rp, const void* tmap, const void* qmap, int num_sms, cudaStream_t s) {
-    auto kern = rp.metric == METRIC_L2 ? (rp.nsub == 4 ? scan_kernel<METRIC_L2, true> : scan_kernel<METRIC_L2, false>)
-                                       : (rp.nsub == 4 ? scan_kernel<METRIC_IP, true> : scan_kernel<METRIC_IP, false>);
+    void (*kern)(RoundParams, const CUtensorMap, const CUtensorMap);
+    if (rp.metric == METRIC_L2)
+        kern = rp.nsub == 4 ? scan_kernel<METRIC_L2, 4> : rp.nsub == 2 ? scan_kernel<METRIC_L2, 2> : scan_kernel<METRIC_L2, 1>;
+    else
+        kern = rp.nsub == 4 ? scan_kernel<METRIC_IP, 4> : rp.nsub == 2 ? scan_kernel<METRIC_IP, 2> : scan_kernel<METRIC_IP, 1>;
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
     kern<<<num_sms, THREADS, SCAN_SMEM, s>>>(rp, *reinterpret_cast<const CUtensorMap*>(tmap),
                                             *reinterpret_cast<const CUtensorMap*>(qmap));

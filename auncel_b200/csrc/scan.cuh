@@ -59,8 +59,8 @@ struct RoundParams {
     const int* active;    // n_active -> query
     int n_active;
     int r0, w, S;
-    int qt;               // queries per scan tile this round: 32 (wide) or 8 (narrow)
-    int nsub;             // sub-slots per (query, rank, segment): 4 in narrow rounds, else 1
+    int qt;               // queries per scan tile this round: 32 / nsub
+    int nsub;             // sub-slots per (query, rank, segment) = row subsets of the scan tile (1, 2 or 4)
     int unsorted;         // 1: slots were filled by rerank_kernel in arrival order (tensor-core rounds)
     int* pair_flag;       // tensor-core rounds: per slot, 1 = overflowed -> redo this pair with the exact scan
     int filtered;         // plan only the flagged pairs
