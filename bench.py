@@ -345,7 +345,7 @@ def cpu_baseline(a, S, np_gpu, D_gpu):
                 "sample": "oracle/_ref/libauncel_ref.so missing"}
     cores = os.cpu_count() or 1
     nround = max(10, (a.nq // 10) * 10)
-    nsample = a.cpu_sample or min(nround, max(40, (4 * cores) // 10 * 10))
+    nsample = a.cpu_sample or min(nround, max(200, (8 * cores) // 10 * 10))
     R, O = build_reference(a, S)
     dt, D, mynp = cpu_sample_search(a, S, R, O, nsample, cores)
     R.close()
@@ -372,7 +372,7 @@ def run_reference(a):
     W = S["W"]
     d = W.SHAPES[a.shape]["d"]
     cores = os.cpu_count() or 1
-    nsample = a.cpu_sample or min(max(10, a.nq // 10 * 10), max(40, (4 * cores) // 10 * 10))
+    nsample = a.cpu_sample or min(max(10, a.nq // 10 * 10), max(200, (8 * cores) // 10 * 10))
     R, O = build_reference(a, S)
     times = []
     for i in range(a.warmup + a.steps):
