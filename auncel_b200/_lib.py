@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libauncel_b200.so")
+LIB_PATH = os.environ.get("AUNCEL_LIB", os.path.join(HERE, "libauncel_b200.so"))  # override: kernel experiments
 
 _f = C.POINTER(C.c_float)
 _l = C.POINTER(C.c_int64)

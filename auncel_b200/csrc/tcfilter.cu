@@ -27,9 +27,15 @@
 namespace auncel {
 
 constexpr int TC_THREADS = 224;   // + warp 6: tile scheduler (decodes tiles one ahead of the TMA warp)
-constexpr int TC_ASTAGES = 5;
+#ifndef TC_ASTAGES_CFG
+#define TC_ASTAGES_CFG 5
+#endif
+#ifndef TC_BKB_CFG
+#define TC_BKB_CFG 128
+#endif
+constexpr int TC_ASTAGES = TC_ASTAGES_CFG;
 constexpr int TC_A_BYTES = 128 * 128;        // 128 rows x 32 f32
-constexpr int TC_B_MAX = 128 * 1024;         // resident query tile: nchunk x N x 128 B
+constexpr int TC_B_MAX = TC_BKB_CFG * 1024;  // resident query tile: nchunk x N x 128 B
 constexpr int TC_NMAX = 256;
 constexpr size_t TC_SMEM = 1024 + TC_B_MAX + (size_t)TC_ASTAGES * TC_A_BYTES + 2 * (TC_NMAX * 8 + 64);
 

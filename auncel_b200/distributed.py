@@ -68,6 +68,38 @@ class ReplicaGroup:
         return torch.cat(Dall)[:n].cpu().numpy(), torch.cat(Iall)[:n].cpu().numpy()
 
 
+class BoundedShardGroup:
+    """Error-bounded search over database shards with the reference's distributed semantics
+    (Auncel/dist/worker.cpp:153-231,243-267, dist/reduce.cpp:98-119): every worker is an
+    independent Auncel index over its slice -- its own calibration against its own ground
+    truth, its own termination -- and the per-worker top-k tables are merged at the end.  One
+    exchange step: an all_gather of (n x k) distances / labels, then merge_tables."""
+
+    def __init__(self, error_sys, metric, group=None, merge_fn=None):
+        self.es, self.shards = error_sys, ShardGroup(_EsAdapter(error_sys), metric, group, merge_fn=merge_fn)
+
+    def search(self, start, n):
+        import torch
+        D, I = self.es.search(start, n)
+        dev = torch.device("cuda", self.es.index.device) if self.shards.dist.is_initialized() and \
+            self.shards.dist.get_backend(self.shards.group) == "nccl" else torch.device("cpu")
+        x_t = torch.zeros(n, 1, device=dev)
+        self.shards.index.tables = (torch.from_numpy(D).to(dev), torch.from_numpy(I).to(dev))
+        Dm, Im = self.shards.search_device(x_t, D.shape[1])
+        return Dm.cpu().numpy(), Im.cpu().numpy()
+
+
+class _EsAdapter:
+    """lets ShardGroup gather tables that Error_sys.search already produced"""
+
+    def __init__(self, es):
+        self.es, self.tables = es, None
+
+    def search_device(self, x_t, k, D_t, I_t):
+        D_t.copy_(self.tables[0])
+        I_t.copy_(self.tables[1])
+
+
 class ShardGroup:
     def __init__(self, index, metric, group=None, translations=None, merge_fn=None, device=None):
         import torch.distributed as dist

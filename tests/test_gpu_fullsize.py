@@ -1,0 +1,122 @@
+"""GPU, BASELINE.json full size (10M x 128, nlist 4096): size-independent properties of the
+path, where the CPU oracle cannot follow.
+
+* exhaustive search (nprobe = nlist) is idempotent ground truth: every fixed-nprobe result is
+  elementwise >= it, sorted, and recall grows with nprobe;
+* engine switches never change bits: tensor-core filter on/off, tie replay on/off only at ties,
+  small vs large scratch budget (different round schedule);
+* shards: two sub-indexes (id % 2) merged == the single index (tests/test_merge.cpp invariant);
+* error-bounded search: latency mode (one query per call) == batch mode; stale my_nprobe replay;
+  ndis statistic == sum of the scanned list sizes.
+"""
+import numpy as np
+import pytest
+import torch
+
+import auncel_b200 as ab
+from auncel_b200 import workload as W
+
+pytestmark = pytest.mark.gpu
+
+NB, NLIST, K = 10_000_000, 4096, 100
+
+
+@pytest.fixture(scope="module")
+def big():
+    dev = torch.device("cuda:0")
+    base = W.make_vectors("sift", NB, 123, dev)
+    q = W.make_vectors("sift", 1200, 789, dev)
+    ix = W.build_index(ab, "sift", base, NLIST, 0, niter=4)
+    gD, gI = W.ground_truth(ix, q, K)
+    es = ab.Error_sys(ix, 1200, K)
+    es.set_gt(gD.cpu().numpy(), gI.cpu().numpy())
+    es.sys_train(600, q[:600].cpu().numpy())
+    return dict(dev=dev, base=base, q=q, ix=ix, gD=gD.cpu().numpy(), gI=gI.cpu().numpy(), es=es)
+
+
+def _fixed(ix, q, nprobe, k=K):
+    D = torch.empty(q.shape[0], k, device=q.device)
+    I = torch.empty(q.shape[0], k, device=q.device, dtype=torch.int64)
+    ix.nprobe = nprobe
+    ix.search_device(q, k, D, I)
+    return D.cpu().numpy(), I.cpu().numpy()
+
+
+def test_fixed_nprobe_properties(big):
+    ix, q, gD = big["ix"], big["q"][600:], big["gD"][600:]
+    prev_recall = -1.0
+    for nprobe in (1, 8, 64):
+        D, I = _fixed(ix, q, nprobe)
+        assert np.all(np.diff(D, axis=1) >= 0), "rows must be sorted best-first"
+        assert np.all(D >= gD - 0.0), "no result can beat the exhaustive search"
+        assert np.all(I >= 0) and np.all(I < NB)
+        for row in I[:50]:
+            assert len(set(row.tolist())) == K, "labels are unique"
+        rec = W.recall_at(gD, D, 10, 1).mean()
+        assert rec > prev_recall
+        prev_recall = rec
+    assert prev_recall > 0.9
+    # tensor-core filter off: identical bits
+    ix.set_option("tensor_core_filter", 0)
+    D0, I0 = _fixed(ix, q, 64)
+    ix.set_option("tensor_core_filter", 1)
+    assert np.array_equal(D0, D) and np.array_equal(I0, I)
+    # different scratch budget -> different round schedule, same bits
+    ix.set_pool_budget(64 << 20)
+    D1, I1 = _fixed(ix, q, 64)
+    ix.set_pool_budget(4 << 30)
+    assert np.array_equal(D1, D) and np.array_equal(I1, I)
+
+
+def test_bounded_search_properties(big):
+    ix, q, es, gD = big["ix"], big["q"], big["es"], big["gD"]
+    acc = np.full(1200, 0.9, np.float32)
+    es.set_topk(10)
+    es.setparam(7.9, 6.0)
+    es.set_queries(600, q.cpu().numpy(), acc, 1200)
+    D, I = es.search(600)
+    mynp = es.my_nprobe[600:].copy()
+    st = ix.stats()
+    assert st["tc_rounds"] > 0 and st["err_bits"] == 0
+    assert np.all(np.diff(D, axis=1) >= 0) and np.all(D >= gD[600:])
+    rec = W.recall_at(gD[600:], D, 10, 1)
+    assert (rec >= 0.9 - 1e-6).mean() > 0.95  # the authors' hyper-parameters hold the bound on this data
+    # ndis == sum of the sizes of the lists each query scanned (IndexIVF.cpp:676)
+    sizes = ix.list_sizes()
+    _, keys = ix.coarse_search(q[600:].cpu().numpy(), NLIST)
+    stop = np.minimum(mynp.astype(np.int64), NLIST)
+    expect = sum(int(sizes[keys[i, :stop[i]]].sum()) for i in range(600))
+    assert int(st["ndis"]) == expect
+    # switches: tensor cores off / tie replay irrelevant without ties in range -> same bits
+    ix.set_option("tensor_core_filter", 0)
+    es.set_queries(600, q.cpu().numpy(), acc, 1200)
+    D0, I0 = es.search(600)
+    ix.set_option("tensor_core_filter", 1)
+    assert np.array_equal(D0, D) and np.array_equal(I0, I) and np.array_equal(es.my_nprobe[600:], mynp)
+    # latency mode == batch mode (eval/bound.cpp:390-396 vs effect_error.cpp:294)
+    es.set_queries(600, q.cpu().numpy(), acc, 1200)
+    for i in range(600, 632):
+        D1, I1 = es.search(i, 1)
+        assert np.array_equal(D1[0], D[i - 600]) and np.array_equal(I1[0], I[i - 600])
+    assert np.array_equal(es.my_nprobe[600:632], mynp[:32])
+    # stale my_nprobe is replayed
+    D2, I2 = es.search(600, 32)
+    assert np.array_equal(D2, D[:32])
+
+
+def test_shards_equal_single_index(big):
+    ix, q, base = big["ix"], big["q"][600:900], big["base"]
+    cent = ix.centroids()
+    ids = np.arange(NB, dtype=np.int64)
+    Dref, Iref = _fixed(ix, q, 16, 10)
+    tabs = []
+    for s in range(2):
+        sub = ab.IndexIVFFlat(128, NLIST, ab.METRIC_L2)
+        sub.set_centroids(cent, compute_interdis=False)
+        sel = torch.arange(s, NB, 2, device=base.device)
+        sub.add_device(base[sel].contiguous(), ids[s::2])
+        tabs.append(_fixed(sub, q, 16, 10))
+        del sub
+    D, I = ab.merge_tables(ab.METRIC_L2, np.stack([t[0] for t in tabs]), np.stack([t[1] for t in tabs]))
+    assert np.array_equal(D, Dref)
+    assert (I == Iref).mean() > 0.9999

@@ -49,6 +49,35 @@ def _worker(rank, world, port, out):
         assert np.array_equal(Dr, Dref[base:base + len(Dr)]) and np.array_equal(Ir, Iref[base:base + len(Ir)])
         Dg, Ig = rg.search_gathered(xq, k)
         assert np.array_equal(Dg, Dref)
+        # error-bounded search over shards, dist/ semantics: every worker calibrates and terminates
+        # on its own slice; tables merged at the end.  Both ranks rebuild both shards to check.
+        from oracle import oracle as O
+        k2, qk = 16, 4
+        xq2 = synth.clustered(22, 200, d, 30)
+        per_shard = []
+        for r in range(world):
+            m_r = AD.shard_mask(ids, world, r)
+            sh = ab.IndexIVFFlat(d, nlist, ab.METRIC_L2, device=rank)
+            sh.set_centroids(cent)
+            sh.add_with_ids(xb[m_r], ids[m_r])
+            sh.nprobe = nlist
+            gD, gI = sh.search(xq2, k2)
+            es = ab.Error_sys(sh, 200, k2)
+            es.set_gt(gD, gI)
+            es.sys_train(100, xq2)
+            es.set_topk(qk)
+            es.setparam(2.0, 1.0)
+            es.set_queries(100, xq2, np.full(200, 0.9, np.float32), 200)
+            per_shard.append(es)
+        mine_es = per_shard[rank]
+        bg = AD.BoundedShardGroup(mine_es, ab.METRIC_L2)
+        Dm, Im = bg.search(100, 100)
+        tabs = []
+        for r in range(world):
+            per_shard[r].set_queries(100, xq2, np.full(200, 0.9, np.float32), 200)
+            tabs.append(per_shard[r].search(100, 100))
+        De, Ie = O.merge_tables(O.L2, np.stack([t[0] for t in tabs]), np.stack([t[1] for t in tabs]))
+        assert np.array_equal(Dm, De) and np.array_equal(Im, Ie)
         out[rank] = "ok"
     finally:
         dist.destroy_process_group()
