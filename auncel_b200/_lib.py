@@ -31,6 +31,9 @@ SYMBOLS = {
     "auncel_index_assign": (C.c_int, [_h, C.c_int64, _f, _l]),
     "auncel_index_reset": (C.c_int, [_h]),
     "auncel_index_list_sizes": (C.c_int, [_h, _l]),
+    "auncel_index_get_lists": (C.c_int, [_h, _f, _l]),
+    "auncel_index_get_params": (C.c_int, [_h, _f, _f]),
+    "auncel_index_has_interdis": (C.c_int, [_h]),
     "auncel_index_coarse_search": (C.c_int, [_h, C.c_int64, _f, C.c_int64, _f, _l]),
     "auncel_index_search": (C.c_int, [_h, C.c_int64, _f, C.c_int64, C.c_int64, C.c_int64, _f, _l]),
     "auncel_index_search_device": (C.c_int, [_h, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,

@@ -381,6 +381,28 @@ int auncel_index_reset(AuncelIndex* idx) {
     API_CATCH
 }
 
+int auncel_index_get_lists(const AuncelIndex* idx, float* codes, int64_t* ids) {
+    API_TRY
+    LOCK(const_cast<AuncelIndex*>(idx));
+    const IvfIndex& ix = idx->ix;
+    CUDA_CHECK(cudaSetDevice(ix.device));
+    const long long nt = ix.h_list_off[ix.nlist];
+    if (nt == 0) return 0;
+    if (codes)
+        CUDA_CHECK(cudaMemcpy2D(codes, ix.d * sizeof(float), ix.codes.p, ix.dpad * sizeof(float), ix.d * sizeof(float),
+                                nt, cudaMemcpyDeviceToHost));
+    if (ids) CUDA_CHECK(cudaMemcpy(ids, ix.ids.p, nt * sizeof(long long), cudaMemcpyDeviceToHost));
+    API_CATCH
+}
+
+int auncel_index_get_params(const AuncelIndex* idx, float* multipler, float* std_m) {
+    *multipler = idx->ix.multipler;
+    *std_m = idx->ix.std_m;
+    return 0;
+}
+
+int auncel_index_has_interdis(const AuncelIndex* idx) { return idx->ix.have_interdis ? 1 : 0; }
+
 int auncel_index_list_sizes(const AuncelIndex* idx, int64_t* out) {
     for (long l = 0; l < idx->ix.nlist; l++) out[l] = idx->ix.h_list_off[l + 1] - idx->ix.h_list_off[l];
     return 0;

@@ -75,6 +75,13 @@ int auncel_index_reset(AuncelIndex* idx);
 /* InvertedLists::list_size for every list (InvertedLists.h:43) */
 int auncel_index_list_sizes(const AuncelIndex* idx, int64_t* out);
 
+/* ArrayInvertedLists contents (InvertedLists.h:182-202) in list order: codes (sum of list sizes x d
+ * floats) and ids; either pointer may be NULL.  What index_io's write_InvertedLists stores
+ * (index_io.cpp:280-330). */
+int auncel_index_get_lists(const AuncelIndex* idx, float* codes, int64_t* ids);
+int auncel_index_get_params(const AuncelIndex* idx, float* multipler, float* std_m);
+int auncel_index_has_interdis(const AuncelIndex* idx);
+
 /* quantizer->search(n, x, nprobe, coarse_dis, idx) (IndexFlat.cpp:42-56): the nprobe best
  * centroids per query, best first, with the reference's exact per-pair arithmetic
  * (knn_L2sqr_sse / knn_inner_product_sse, utils.cpp:417-490). */
