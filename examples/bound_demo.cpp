@@ -5,6 +5,7 @@
 // invariants of tests/test_merge.cpp and tests/test_threaded_index.cpp.
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <random>
 #include <sys/time.h>
 
@@ -44,8 +45,9 @@ int main(int argc, char** argv) {
     std::vector<float> xb = gen(nb), xq = gen(ts + ses);
     double t0 = elapsed();
     try {
-        faiss::IndexFlatL2 quantizer(d);
-        faiss::IndexIVFFlat index(&quantizer, d, nlist, faiss::METRIC_L2);
+        std::unique_ptr<faiss::Index> index_p(faiss::index_factory(d, "IVF1024,Flat"));  // bound.cpp:220
+        faiss::IndexIVFFlat& index = *dynamic_cast<faiss::IndexIVFFlat*>(index_p.get());
+        faiss::IndexFlat& quantizer = *dynamic_cast<faiss::IndexFlat*>(index.quantizer);
         index.niter = 8;
         index.set_tune_mode();  // bound.cpp:261-263
         index.train(nb, xb.data());

@@ -396,4 +396,16 @@ struct IndexReplicas : ThreadedIndexBase {
     }
 };
 
+/// index_factory (AutoTune.cpp:741-852) for the one description this path uses: "IVF<nlist>,Flat"
+/// (eval/bound.cpp:220).  The returned IndexIVFFlat owns its IndexFlat quantizer.
+inline Index* index_factory(int d, const char* description, MetricType metric = METRIC_L2) {
+    int nlist = 0, consumed = 0;
+    if (std::sscanf(description, "IVF%d,Flat%n", &nlist, &consumed) != 1 || description[consumed] != '\0' || nlist <= 0)
+        throw FaissException(std::string("index_factory: could not parse the description ") + description);
+    Index* quantizer = metric == METRIC_L2 ? (Index*)new IndexFlatL2(d) : (Index*)new IndexFlatIP(d);
+    IndexIVFFlat* ix = new IndexIVFFlat(quantizer, d, nlist, metric);
+    ix->own_fields = true;
+    return ix;
+}
+
 }  // namespace faiss
