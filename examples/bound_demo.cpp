@@ -103,7 +103,7 @@ int main(int argc, char** argv) {
         }
 
         // shards: 3 sub-indexes sharing the centroids == the single index (tests/test_merge.cpp:94-152)
-        index.nprobe = 8;
+        faiss::set_index_parameters(&index, "nprobe=8,max_codes=0");  // AutoTune.cpp:455-563
         std::vector<float> Dref(ses * 10);
         std::vector<faiss::Index::idx_t> Iref(ses * 10);
         index.search(ses, xq.data() + ts * d, 10, Dref.data(), Iref.data());

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <fstream>
@@ -395,6 +396,28 @@ struct IndexReplicas : ThreadedIndexBase {
         });
     }
 };
+
+/// ParameterSpace::set_index_parameters (AutoTune.cpp:455-563) for the IVF parameters of this path:
+/// a comma-separated "nprobe=16,max_codes=0" string.
+inline void set_index_parameters(Index* index, const char* description) {
+    IndexIVF* ix = dynamic_cast<IndexIVF*>(index);
+    AUNCEL_FAISS_THROW_IF_NOT_MSG(ix != nullptr, "set_index_parameters: not an IndexIVF");
+    std::string s(description);
+    size_t pos = 0;
+    while (pos < s.size()) {
+        size_t end = s.find(',', pos);
+        if (end == std::string::npos) end = s.size();
+        std::string tok = s.substr(pos, end - pos);
+        size_t eq = tok.find('=');
+        AUNCEL_FAISS_THROW_IF_NOT_MSG(eq != std::string::npos, "could not parse parameter " + tok);
+        std::string name = tok.substr(0, eq);
+        double val = std::atof(tok.c_str() + eq + 1);
+        if (name == "nprobe") ix->nprobe = (size_t)val;
+        else if (name == "max_codes") ix->max_codes = std::isfinite(val) ? (size_t)val : 0;
+        else throw FaissException("ParameterSpace::set_index_parameter: could not set parameter " + name);
+        pos = end + 1;
+    }
+}
 
 /// index_factory (AutoTune.cpp:741-852) for the one description this path uses: "IVF<nlist>,Flat"
 /// (eval/bound.cpp:220).  The returned IndexIVFFlat owns its IndexFlat quantizer.

@@ -69,3 +69,15 @@ def test_write_read_roundtrip_gpu(tmp_path):
     assert np.array_equal(D1, D2) and np.array_equal(I1, I2) and np.array_equal(np1, np2)
     p = IO.parse_ivfflat(open(f, "rb").read())
     assert p["auncel"] is not None and len(p["auncel"]["traces"]) == len(ix.traces())
+
+
+def test_vecs_roundtrip(tmp_path):
+    from auncel_b200 import vecs_io
+    x = synth.clustered(9, 37, 12)
+    f = str(tmp_path / "x.fvecs")
+    vecs_io.fvecs_write(f, x)
+    assert np.array_equal(vecs_io.fvecs_read(f), x)
+    ids = (np.arange(37 * 5).reshape(37, 5) * 3).astype(np.int32)
+    g = str(tmp_path / "i.ivecs")
+    vecs_io.fvecs_write(g, ids)
+    assert np.array_equal(vecs_io.ivecs_read(g), ids)
