@@ -253,6 +253,35 @@ __device__ __forceinline__ float key_dist(unsigned long long key) {
     return ord2f(o);
 }
 
+// one 32-dimension chunk of NQ queries x TV rows per lane, in the reference's accumulation order
+template <int METRIC, int TV, int NQ>
+__device__ __forceinline__ void dist_chunk(float (&acc)[4][TV][4], const float* sq, const unsigned char* sv, int nkc,
+                                           int xr) {
+#pragma unroll 2
+    for (int kc = 0; kc < nkc; kc++) {
+        float4 a[NQ], b[TV];
+#pragma unroll
+        for (int i = 0; i < NQ; i++) a[i] = *reinterpret_cast<const float4*>(sq + i * QLD + kc * 4);
+#pragma unroll
+        for (int j = 0; j < TV; j++) b[j] = *reinterpret_cast<const float4*>(sv + j * (32 * 128) + ((kc ^ xr) << 4));
+#pragma unroll
+        for (int i = 0; i < NQ; i++)
+#pragma unroll
+            for (int j = 0; j < TV; j++) exact_step<METRIC>(acc[i][j], a[i], b[j]);
+    }
+}
+
+// threshold as an unsigned key where smaller = tighter (atomicMin publishes improvements)
+template <int METRIC>
+__device__ __forceinline__ unsigned tau_key(float tau) {
+    uint32_t o = f2ord(tau);
+    return METRIC == METRIC_L2 ? o : ~o;
+}
+template <int METRIC>
+__device__ __forceinline__ float key_tau(unsigned k) {
+    return ord2f(METRIC == METRIC_L2 ? k : ~k);
+}
+
 // sort the buffer, keep the K best, tighten tau when K are held
 template <int METRIC>
 __device__ __forceinline__ void compact(unsigned long long* buf, int& cnt, float& tau, int K, int lane) {
@@ -283,6 +312,10 @@ template <int METRIC, int RSPLIT>
 __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap qmap) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES];
+    // thresholds shared by the RSPLIT warps that scan different rows for the same query: a warp
+    // that has K candidates publishes its K-th best, the others filter with the tightest value.
+    // Ring of 8 tiles (> STAGES, the furthest a warp can run ahead), reset by the producer.
+    __shared__ unsigned s_tau[8][SCAN_QT];
     unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned long long* cand = reinterpret_cast<unsigned long long*>(smem + (size_t)STAGES * STAGE_BYTES);
 
@@ -302,7 +335,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
         // =========================== producer ===========================
         const int nchunk = (dpad + SCAN_DK - 1) / SCAN_DK;
         const int total_tiles = rp.ctl[CTL_TOTAL_TILES];
-        unsigned it = 0;
+        unsigned it = 0, tcount = 0;
         while (true) {
             int T = 0;
             if (lane == 0) T = atomicAdd(&rp.ctl[CTL_TILE_COUNTER], 1);
@@ -362,6 +395,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
                     }
                     h->slot[lane] = slot;
                     h->tau[lane] = tau;
+                    if (blk == 0 && c == 0) s_tau[tcount & 7][lane] = tau_key<METRIC>(tau);
                     __syncwarp();
                     if (lane == 0) {
                         mbar_expect_tx(&full_bar[s], (unsigned)(VT_BYTES + QT_BYTES));
@@ -370,6 +404,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
                     }
                 }
             }
+            tcount++;
         }
         // end marker
         {
@@ -386,7 +421,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
 
     // =========================== consumers ===========================
     constexpr int TV = 4 / RSPLIT;                       // list rows per lane
-    const int qbase = (warp / RSPLIT) * 4;               // first query of this warp
+    constexpr int NGROUP = 8 / RSPLIT;                   // warps that share a row subset split the tile's queries
+    const int group = warp / RSPLIT;
     const int rbase = (warp % RSPLIT) * (SCAN_VT / RSPLIT);  // first row of this warp (rows rbase + lane + 32 j)
     int cnt[4] = {0, 0, 0, 0};
     float tau[4] = {0.f, 0.f, 0.f, 0.f};
@@ -398,6 +434,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
 #pragma unroll
             for (int x = 0; x < 4; x++) acc[i][j][x] = 0.f;
     const int xr = lane & 7;  // SWIZZLE_128B: 16-byte chunk index is XORed with (row & 7)
+    unsigned tcount = 0;
+    int tslot = 0;
 
     for (unsigned it = 0;; it++) {
         const int s = it % STAGES;
@@ -405,37 +443,37 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
         const unsigned char* st = smem + (size_t)s * STAGE_BYTES;
         const StageHdr* h = reinterpret_cast<const StageHdr*>(st + VT_BYTES + QT_BYTES);
         if (h->flags) break;
+        // the tile's Qt queries are dealt evenly to the query groups (<= 4 each), so partially
+        // filled tiles keep every warp busy instead of filling group 0 first
         const int Qt = h->Qt;
-        const bool has_q = qbase < Qt;
+        const int per = (Qt + NGROUP - 1) / NGROUP;
+        const int q0 = group * per;
+        const int nq = max(0, min(per, Qt - q0));
+        const bool has_q = nq > 0;
         const int last_chunk = h->last_chunk, last_iter = h->last_iter;
         const int blk = h->blk, nvec = h->nvec, v_begin = h->v_begin, nk = h->nk;
         int slot[4];
         if (h->first) {
+            tslot = tcount & 7;
+            tcount++;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                tau[i] = h->tau[qbase + i];
+                tau[i] = h->tau[min(q0 + i, SCAN_QT - 1)];
                 cnt[i] = 0;
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) slot[i] = h->slot[qbase + i];
+        for (int i = 0; i < 4; i++) slot[i] = h->slot[min(q0 + i, SCAN_QT - 1)];
 
-        if (has_q) {
+        if (nq > 0) {
             const unsigned char* sv = st + (rbase + lane) * 128;
-            const float* sq = reinterpret_cast<const float*>(st + VT_BYTES) + qbase * QLD;
+            const float* sq = reinterpret_cast<const float*>(st + VT_BYTES) + q0 * QLD;
             const int nkc = nk >> 2;
-#pragma unroll 2
-            for (int kc = 0; kc < nkc; kc++) {
-                float4 a[4], b[TV];
-#pragma unroll
-                for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4*>(sq + i * QLD + kc * 4);
-#pragma unroll
-                for (int j = 0; j < TV; j++)
-                    b[j] = *reinterpret_cast<const float4*>(sv + j * (32 * 128) + ((kc ^ xr) << 4));
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-#pragma unroll
-                    for (int j = 0; j < TV; j++) exact_step<METRIC>(acc[i][j], a[i], b[j]);
+            switch (nq) {  // warp-uniform: only the queries this warp owns are computed
+                case 1: dist_chunk<METRIC, TV, 1>(acc, sq, sv, nkc, xr); break;
+                case 2: dist_chunk<METRIC, TV, 2>(acc, sq, sv, nkc, xr); break;
+                case 3: dist_chunk<METRIC, TV, 3>(acc, sq, sv, nkc, xr); break;
+                default: dist_chunk<METRIC, TV, 4>(acc, sq, sv, nkc, xr); break;
             }
         }
         // the stage's data and header are consumed: hand the slot back to the producer
@@ -446,8 +484,13 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
             // ---- epilogue: filter against tau, append, compact when the buffer fills
 #pragma unroll
             for (int i = 0; i < 4; i++) {
+                if (i >= nq) break;
                 unsigned long long* buf = cand + (size_t)(warp * 4 + i) * CAP;
-                const bool qok = qbase + i < Qt;
+                const bool qok = true;
+                if (RSPLIT > 1) {  // the tightest threshold any sibling warp has published
+                    const float shared_tau = key_tau<METRIC>(s_tau[tslot][q0 + i]);
+                    if (METRIC == METRIC_L2 ? shared_tau < tau[i] : shared_tau > tau[i]) tau[i] = shared_tau;
+                }
 #pragma unroll
                 for (int j = 0; j < TV; j++) {
                     float dist = exact_finish(acc[i][j]);
@@ -458,6 +501,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
                     if (m) {
                         if (cnt[i] + 32 > CAP) {
                             compact<METRIC>(buf, cnt[i], tau[i], K, lane);
+                            if (RSPLIT > 1 && lane == 0) atomicMin(&s_tau[tslot][q0 + i], tau_key<METRIC>(tau[i]));
                             pass = pass && (METRIC == METRIC_L2 ? dist < tau[i] : dist > tau[i]);
                             m = __ballot_sync(0xffffffffu, pass);
                         }
@@ -472,7 +516,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
             // ---- per-(query, segment[, row subset]) result: sorted, at most K candidates
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                if (qbase + i < Qt && cnt[i] > 0) {
+                if (i < nq && cnt[i] > 0) {
                     unsigned long long* buf = cand + (size_t)(warp * 4 + i) * CAP;
                     const long sl = (long)slot[i] * RSPLIT + (warp % RSPLIT);
                     if (cnt[i] <= 32) {
