@@ -266,6 +266,32 @@ __device__ __forceinline__ void heap_push_dev(int k, unsigned long long* h, unsi
 // until it meets real values.  That prefix does not depend on the data, only on how many
 // elements were inserted: `entry[j]` is the node where insertion j meets its first real
 // comparison (precomputed on the host, heap_entry_table), so the replay starts there.
+__device__ __forceinline__ uint32_t node_ord(unsigned long long a) { return (uint32_t)(a >> 32); }
+
+// One level of heap_pop's sift-down (Heap.h:96-113) for the pop a lane carries; see the pipeline
+// in heap_order_kernel.  Children are one aligned 16-byte load (the heap array is 1-based).
+struct PopLane {
+    unsigned long long v, top;
+    int node, size, depth;
+    bool busy;
+};
+__device__ __forceinline__ void pop_step(PopLane& p, unsigned long long* h, int k) {
+    // written without branches: a lone warp pays ~20 cycles per taken branch
+    const int i1 = p.node << 1;
+    const ulonglong2 cc = *reinterpret_cast<const ulonglong2*>(&h[min(i1, k) & ~1]);  // in bounds; unused if i1 > size
+    const bool has1 = i1 <= p.size, has2 = i1 < p.size;
+    const bool left = !has2 | (node_ord(cc.x) > node_ord(cc.y));
+    const unsigned long long c = left ? cc.x : cc.y;
+    const bool stop = !has1 | (node_ord(p.v) > node_ord(c));
+    if (p.busy) h[p.node] = stop ? p.v : c;
+    if (p.busy & stop) h[p.size] = p.top;  // slot `size` is free after the pop: bh_val[k-ii-1] = top (Heap.h:305-317)
+    p.busy = p.busy & !stop;
+    p.node = stop ? p.node : i1 + (left ? 0 : 1);
+    p.depth += stop ? 0 : 1;
+}
+
+// A single warp is latency-bound on its own dependent instructions (~5 cycles each), so the
+// replay is written for few instructions per heap level, not for few memory round trips.
 template <int METRIC>
 __global__ void __launch_bounds__(32)
 heap_order_kernel(const float* __restrict__ raw, long nlist, int k, const int* __restrict__ entry,
@@ -279,19 +305,77 @@ heap_order_kernel(const float* __restrict__ raw, long nlist, int k, const int* _
     const float neut = METRIC == METRIC_L2 ? FLT_MAX : -FLT_MAX;
     uint32_t on = f2ord(neut);
     if (METRIC == METRIC_IP) on = ~on;
-    for (int i = lane; i <= k; i += 32) hp[i] = ((unsigned long long)on << 32) | 0xffffffffu;  // heapify, id -1
+    const unsigned long long neutral = ((unsigned long long)on << 32) | 0xffffffffu;  // heapify, id -1
+    for (int i = lane; i <= k + 1; i += 32) hp[i] = neutral;
     __syncwarp();
+#ifdef HEAP_TIMING
+    long long t0 = clock64();
+#endif
+    // Fill phase.  Insertion j (0 < j < k) pops with v = h[k] = d[j-1] (the previous push stays at
+    // slot k as long as its parent is neutral), drops it into node entry[j] and sifts it down inside
+    // that node's subtree, whose nodes were all filled earlier.  Sift-downs in disjoint subtrees
+    // commute, so for the prefix j <= J whose entries stay off the root-to-k path (J = entry[k],
+    // heap_entry_table; all but the last log2(k)+1 insertions when k is a power of two) the warp
+    // places every d[j-1] at once and sifts level by level, deepest first -- Floyd's heapify with
+    // the reference's comparisons.  The rest runs serially below.
+    const float* row = raw + q * nlist;
+    int J = min(entry[k], (int)min((long)k, nlist) - 1);
+    {
+        bool bad = false;  // a distance that does not beat the neutral top is not inserted: no shortcut
+        for (int j = lane; j <= J; j += 32) {
+            uint32_t o = f2ord(__ldg(row + j));
+            if (METRIC == METRIC_IP) o = ~o;
+            bad |= !(o < on);
+        }
+        if (__any_sync(0xffffffffu, bad)) J = 0;
+    }
+    if (J >= 1) {
+        for (int j = 1 + lane; j <= J; j += 32) {
+            uint32_t o = f2ord(__ldg(row + j - 1));
+            if (METRIC == METRIC_IP) o = ~o;
+            h[__ldg(entry + j)] = ((unsigned long long)o << 32) | (unsigned)(j - 1);
+        }
+        __syncwarp();
+        const int dk = 31 - __clz(k);
+        for (int t = dk - 1; t >= 0; t--) {
+            const int first = 1 << t;
+            for (int base = 0; base < first; base += 32) {
+                int i = first + base + lane;
+                const unsigned long long v = base + lane < first ? h[i] : neutral;
+                bool active = v != neutral;
+                for (int lev = t; lev < dk && __any_sync(0xffffffffu, active); lev++) {
+                    const int i1 = i << 1;
+                    const ulonglong2 cc = *reinterpret_cast<const ulonglong2*>(&h[min(i1, k) & ~1]);
+                    const bool left = node_ord(cc.x) > node_ord(cc.y);
+                    const unsigned long long c = left ? cc.x : cc.y;
+                    const bool stop = (i1 > k) | (node_ord(v) > node_ord(c));
+                    if (active) h[i] = stop ? v : c;
+                    active = active & !stop;
+                    i = stop ? i : i1 + (left ? 0 : 1);
+                }
+                if (active) h[i] = v;  // unreachable: a sift-down ends at a leaf at the latest
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            uint32_t o = f2ord(__ldg(row + J));
+            if (METRIC == METRIC_IP) o = ~o;
+            h[k] = ((unsigned long long)o << 32) | (unsigned)J;  // push J stays at slot k
+        }
+        __syncwarp();
+    }
     if (lane == 0) {
-        const float* row = raw + q * nlist;
         constexpr int PF = 8;  // software prefetch of the distance row
+        const long jstart = J >= 1 ? J + 1 : 0;
         float buf[PF];
         int ebuf[PF];
 #pragma unroll
         for (int t = 0; t < PF; t++) {
-            buf[t] = t < nlist ? __ldg(row + t) : 0.f;
-            ebuf[t] = t < k ? __ldg(entry + t) : 1;
+            buf[t] = jstart + t < nlist ? __ldg(row + jstart + t) : 0.f;
+            ebuf[t] = jstart + t < k ? __ldg(entry + jstart + t) : 1;
         }
-        for (long j0 = 0; j0 < nlist; j0 += PF) {
+        unsigned long long last = h[k];  // kept in a register
+        for (long j0 = jstart; j0 < nlist; j0 += PF) {
             float cur[PF];
             int ecur[PF];
 #pragma unroll
@@ -308,20 +392,95 @@ heap_order_kernel(const float* __restrict__ raw, long nlist, int k, const int* _
                 if (j >= nlist) break;
                 uint32_t o = f2ord(cur[t]);
                 if (METRIC == METRIC_IP) o = ~o;
-                if (o < (uint32_t)(h[1] >> 32)) {  // dis < simi[0] (L2) / ip > simi[0] (IP), utils.cpp:441,479
-                    heap_pop_dev(k, h, j < k ? ecur[t] : 1);
-                    heap_push_dev(k, h, ((unsigned long long)o << 32) | (unsigned)j);
+                const unsigned long long nv = ((unsigned long long)o << 32) | (unsigned)j;
+                if (j < k) {
+                    // the root is still neutral: dis < simi[0] (utils.cpp:441,479) unless dis is FLT_MAX itself
+                    if (!(o < on)) continue;
+                    // heap_pop from the end of the neutral prefix, one level per iteration
+                    int i = ecur[t];
+                    while (true) {
+                        const int i1 = i << 1;
+                        if (i1 > k) break;
+                        const ulonglong2 cc = *reinterpret_cast<const ulonglong2*>(&h[i1]);
+                        const bool left = (i1 + 1 > k) || node_ord(cc.x) > node_ord(cc.y);
+                        const unsigned long long c = left ? cc.x : cc.y;
+                        if (node_ord(last) > node_ord(c)) break;
+                        h[i] = c;
+                        i = i1 + (left ? 0 : 1);
+                    }
+                    h[i] = last;
+                    // heap_push at slot k (Heap.h:124-142)
+                    i = k;
+                    last = nv;
+                    while (i > 1) {
+                        const int f = i >> 1;
+                        const unsigned long long par = h[f];
+                        if (!(o > node_ord(par))) break;
+                        h[i] = par;
+                        if (i == k) last = par;
+                        i = f;
+                    }
+                    h[i] = nv;
+                } else if (o < node_ord(h[1])) {  // replacement phase (nprobe < nlist): full-depth pops
+                    heap_pop_dev(k, h, 1);
+                    heap_push_dev(k, h, nv);
                 }
             }
         }
-        // heap_reorder, Heap.h:295-322 (every slot holds a real element because k <= nlist)
-        for (int i = 0; i < k; i++) {
-            const unsigned long long top = h[1];
-            heap_pop_dev(k - i, h);
-            h[k - i] = top;  // slot k-i is free after the pop: same as bh_val[k-ii-1] with ii == i
+    }
+    __syncwarp();
+#ifdef HEAP_TIMING
+    long long t1 = clock64();
+#endif
+    // heap_reorder, Heap.h:295-322 (every slot holds a real element because k <= nlist): pop p
+    // takes top = h[1], sifts v = h[k-p] down a heap of size k-p, then stores top in slot k-p.
+    // The k sift-downs are the bulk of the replay and each is a chain of dependent steps, so they
+    // are software-pipelined over the lanes: a new pop enters at the root every second tick while
+    // the earlier ones are still on their way down.  Every lane moves one level per tick; lanes are
+    // therefore >= 2 levels apart, a lane at depth t reads depth t+1 (final: the lane ahead wrote
+    // it a tick ago) and writes depth t.  The only other dependence is v = h[k-p], a bottom slot an
+    // earlier pop may still be heading for: a pop starts only when no lane in flight sits on an
+    // ancestor of that slot (a lane that has left the ancestor chain can never come back to it).
+    // Pop p runs on lane p % 32: a pop lasts at most log2(k)+2 ticks, so that lane is idle again.
+    {
+        PopLane pl;
+        pl.busy = false;
+        pl.node = 1;
+        pl.size = 0;
+        pl.depth = 0;
+        pl.v = pl.top = 0;
+        int next_pop = 0;
+        while (next_pop < k) {
+            const int s = k - next_pop;
+            const int ds = 31 - __clz(s);
+            const bool anc = pl.busy && pl.depth <= ds && (s >> (ds - pl.depth)) == pl.node;
+            if (!__any_sync(0xffffffffu, anc)) {
+                if (lane == (next_pop & 31)) {
+                    pl.busy = true;
+                    pl.node = 1;
+                    pl.depth = 0;
+                    pl.size = s;
+                    pl.v = h[s];
+                    pl.top = h[1];
+                }
+                next_pop++;
+            }
+            pop_step(pl, h, k);
+            __syncwarp();
+            pop_step(pl, h, k);
+            __syncwarp();
+        }
+        const int drain = 34 - __clz(k);
+        for (int t = 0; t < drain; t++) {
+            pop_step(pl, h, k);
+            __syncwarp();
         }
     }
     __syncwarp();
+#ifdef HEAP_TIMING
+    if (lane == 0 && blockIdx.x == 0)
+        printf("heap_order: nfix %d k %d phase1 %lld cycles, phase2 %lld cycles\n", *nfix, k, t1 - t0, clock64() - t1);
+#endif
     for (int i = lane; i < k; i += 32) {
         const unsigned long long node = hp[i + 1];
         uint32_t o = (uint32_t)(node >> 32);
@@ -334,7 +493,7 @@ heap_order_kernel(const float* __restrict__ raw, long nlist, int k, const int* _
 
 // entry[j], j < k: see heap_order_kernel.  Pure structure: simulate heap_pop on occupancy bits.
 void heap_entry_table(int k, std::vector<int>& entry) {
-    entry.assign(k, 1);
+    entry.assign(k + 1, 1);
     std::vector<char> real(k + 2, 0);
     for (int j = 0; j < k; j++) {
         // insertion j pops with v = h[k] (neutral for j == 0, real afterwards), then pushes at slot k
@@ -358,6 +517,21 @@ void heap_entry_table(int k, std::vector<int>& entry) {
         }
         real[k] = 1;      // push places d_j at slot k (and may sift up only through real parents)
     }
+    // entry[k] = J: the longest prefix 1..J of insertions whose entry node is not on the path from
+    // the root to slot k.  Until such a node is filled, slot k's parent is neutral (pushes stay at
+    // slot k) and every pop works in a subtree that neither contains slot k nor a neutral node.
+    int J = k - 1;
+    int dk = 0;
+    while ((k >> (dk + 1)) > 0) dk++;
+    for (int j = 1; j < k; j++) {
+        int n = entry[j], dn = 0;
+        while ((n >> (dn + 1)) > 0) dn++;
+        if ((k >> (dk - dn)) == n) {
+            J = j - 1;
+            break;
+        }
+    }
+    entry[k] = std::max(J, 0);
 }
 
 // queries (from `list`, or all n when list == nullptr) whose first tie lies below `bound`

@@ -302,8 +302,8 @@ const int* IvfIndex::entry_table(int k) {
     if (k != heap_entry_k) {
         std::vector<int> e;
         heap_entry_table(k, e);
-        heap_entry.ensure(k);
-        CUDA_CHECK(cudaMemcpyAsync(heap_entry.p, e.data(), k * sizeof(int), cudaMemcpyHostToDevice, stream));
+        heap_entry.ensure(e.size());  // k entries + the length of the parallel prefix
+        CUDA_CHECK(cudaMemcpyAsync(heap_entry.p, e.data(), e.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
         CUDA_CHECK(cudaStreamSynchronize(stream));
         heap_entry_k = k;
     }

@@ -161,7 +161,7 @@ struct StageHdr {
     int Qt;          // queries in the tile
     int v_begin;     // first list offset of the segment
     int nvec;        // vectors in the segment
-    int pad[7];
+    int pad[7];      // (the first eight ints are read by the consumers as two 16-byte loads)
     int slot[SCAN_QT];
     float tau[SCAN_QT];
 };
@@ -257,7 +257,8 @@ __device__ __forceinline__ float key_dist(unsigned long long key) {
 template <int METRIC, int TV, int NQ>
 __device__ __forceinline__ void dist_chunk(float (&acc)[4][TV][4], const float* sq, const unsigned char* sv, int nkc,
                                            int xr) {
-#pragma unroll 2
+    // few (query, row) pairs per lane: unroll deeper so enough loads are in flight
+#pragma unroll(NQ * TV <= 2 ? 8 : NQ * TV <= 4 ? 4 : 2)
     for (int kc = 0; kc < nkc; kc++) {
         float4 a[NQ], b[TV];
 #pragma unroll
@@ -442,18 +443,20 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
         const unsigned char* st = smem + (size_t)s * STAGE_BYTES;
         const StageHdr* h = reinterpret_cast<const StageHdr*>(st + VT_BYTES + QT_BYTES);
-        if (h->flags) break;
+        const int4 h0 = *reinterpret_cast<const int4*>(&h->flags);  // flags, first, last_chunk, last_iter
+        if (h0.x) break;
+        const int4 h1 = *reinterpret_cast<const int4*>(&h->blk);    // blk, nk, Qt, v_begin
         // the tile's Qt queries are dealt evenly to the query groups (<= 4 each), so partially
         // filled tiles keep every warp busy instead of filling group 0 first
-        const int Qt = h->Qt;
+        const int Qt = h1.z;
         const int per = (Qt + NGROUP - 1) / NGROUP;
         const int q0 = group * per;
         const int nq = max(0, min(per, Qt - q0));
         const bool has_q = nq > 0;
-        const int last_chunk = h->last_chunk, last_iter = h->last_iter;
-        const int blk = h->blk, nvec = h->nvec, v_begin = h->v_begin, nk = h->nk;
+        const int last_chunk = h0.z, last_iter = h0.w;
+        const int blk = h1.x, nvec = h->nvec, v_begin = h1.w, nk = h1.y;
         int slot[4];
-        if (h->first) {
+        if (h0.y) {
             tslot = tcount & 7;
             tcount++;
 #pragma unroll
@@ -462,10 +465,16 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
                 cnt[i] = 0;
             }
         }
+        if (last_iter) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) slot[i] = h->slot[min(q0 + i, SCAN_QT - 1)];
+            for (int i = 0; i < 4; i++) slot[i] = h->slot[min(q0 + i, SCAN_QT - 1)];
+        }
 
+#ifdef SCAN_EXP_NODIST
+        if (false) {
+#else
         if (nq > 0) {
+#endif
             const unsigned char* sv = st + (rbase + lane) * 128;
             const float* sq = reinterpret_cast<const float*>(st + VT_BYTES) + q0 * QLD;
             const int nkc = nk >> 2;
@@ -497,6 +506,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
                     acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
                     int v = blk * SCAN_VT + rbase + lane + 32 * j;
                     bool pass = qok && v < nvec && (METRIC == METRIC_L2 ? dist < tau[i] : dist > tau[i]);
+#ifdef SCAN_EXP_NOSELECT
+                    pass = pass && dist == -12345.f;
+#endif
                     unsigned m = __ballot_sync(0xffffffffu, pass);
                     if (m) {
                         if (cnt[i] + 32 > CAP) {
