@@ -14,10 +14,11 @@
 //      recomputes them with the reference's exact arithmetic (exact.cuh) and applies the
 //      reference's strict test.  Results are therefore bit-identical to the SIMT path; the
 //      tensor cores only decide what is worth computing exactly.
-// Warp roles (224 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected lane),
-// warps 2-5 epilogue (TMEM -> registers -> filter), warp 6 tile scheduler (claims and decodes
-// the next tile and its per-query constants while the current one streams).  TMEM: 2 x 256 fp32 columns, double
-// buffered so the MMAs of block b+1 overlap the filter of block b.
+// Warp roles (352 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected lane),
+// warps 2-9 epilogue (TMEM -> registers -> filter; warps 2-5 drain accumulator 0, warps 6-9
+// accumulator 1), warp 10 tile scheduler (claims and decodes the next tile and its per-query
+// constants while the current one streams).  TMEM: 2 x 256 fp32 columns, double buffered so the
+// MMAs of block b+1 overlap the filter of block b.
 #include <cuda.h>
 
 #include "exact.cuh"
@@ -26,7 +27,7 @@
 
 namespace auncel {
 
-constexpr int TC_THREADS = 224;   // + warp 6: tile scheduler (decodes tiles one ahead of the TMA warp)
+constexpr int TC_THREADS = 352;   // TMA, MMA, 2 x 4 epilogue warps (one group per accumulator), tile scheduler
 #ifndef TC_ASTAGES_CFG
 #define TC_ASTAGES_CFG 5
 #endif
@@ -70,6 +71,18 @@ __device__ __forceinline__ void mb_wait(unsigned long long* b, unsigned parity) 
                      : "memory");
     } while (!ok);
 }
+#ifdef TC_TIMING
+// wait-time attribution (debug builds only): cycles spent at each barrier site, printed by CTA 0
+__device__ long long g_tc_wait[16];
+#define MB_WAIT(site, b, par)                        \
+    do {                                             \
+        long long t0_ = clock64();                   \
+        mb_wait(b, par);                             \
+        tc_wait_acc[site] += clock64() - t0_;        \
+    } while (0)
+#else
+#define MB_WAIT(site, b, par) mb_wait(b, par)
+#endif
 __device__ __forceinline__ void tma2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(s32(dst)),
                  "l"(map), "r"(c0), "r"(c1), "r"(s32(bar))
@@ -90,6 +103,13 @@ __device__ __forceinline__ void umma_tf32(unsigned d_tmem, unsigned long long ad
 }
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+// one lane of a converged warp; ptxas knows the guarded region is single-threaded and issues the
+// uniform-operand tcgen05 instructions directly instead of wrapping each in a per-lane loop
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -120,6 +140,10 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
     TileMeta* meta = reinterpret_cast<TileMeta*>(Asm + (size_t)TC_ASTAGES * TC_A_BYTES);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef TC_TIMING
+    long long tc_wait_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long tc_t_begin = clock64();
+#endif
     const int N = ta.N, dpad = rp.dpad;
     const int nchunk = (dpad + 31) / 32;
 
@@ -134,7 +158,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
             mb_init(&t_full[i], 1);
             mb_init(&t_empty[i], 4);
             mb_init(&m_full[i], 1);
-            mb_init(&m_empty[i], 6);  // TMA warp + MMA warp + 4 epilogue warps
+            mb_init(&m_empty[i], 10);  // TMA warp + MMA warp + 8 epilogue warps
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -147,7 +171,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
     tc_fence_after();
     const unsigned tmem_base = tmem_base_s;
 
-    if (warp == 6) {
+    if (warp == 10) {
         // =========================== tile scheduler ===========================
         const int total_tiles = rp.ctl[CTL_TOTAL_TILES];
         for (unsigned t = 0;; t++) {
@@ -194,7 +218,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                     cq[jj] = c;
                 }
             }
-            mb_wait(&m_empty[m], ((t >> 1) & 1) ^ 1);
+            MB_WAIT(0, &m_empty[m], ((t >> 1) & 1) ^ 1);
             if (T >= total_tiles) {
                 if (lane == 0) {
                     mt->flags = 1;
@@ -221,7 +245,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
         unsigned ita = 0;
         for (unsigned t = 0;; t++) {
             const int m = t & 1;
-            mb_wait(&m_full[m], (t >> 1) & 1);
+            MB_WAIT(1, &m_full[m], (t >> 1) & 1);
             const int flags = meta[m].flags, nblk = meta[m].nblk, pair0 = meta[m].pair0;
             const long long L0 = meta[m].row0;
             __syncwarp();
@@ -229,13 +253,13 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
             if (flags) break;
             if (lane == 0) {
                 // queries: resident for the whole tile, one swizzled [N x 32] block per k-chunk
-                mb_wait(&b_empty, (t & 1) ^ 1);
+                MB_WAIT(2, &b_empty, (t & 1) ^ 1);
                 mb_expect_tx(&b_full, (unsigned)(nchunk * N * 128));
                 for (int c = 0; c < nchunk; c++) tma2d(Bsm + (size_t)c * N * 128, &bmap, c * 32, pair0, &b_full);
                 for (int blk = 0; blk < nblk; blk++)
                     for (int c = 0; c < nchunk; c++, ita++) {
                         const int s = ita % TC_ASTAGES;
-                        mb_wait(&a_empty[s], ((ita / TC_ASTAGES) & 1) ^ 1);
+                        MB_WAIT(3, &a_empty[s], ((ita / TC_ASTAGES) & 1) ^ 1);
                         mb_expect_tx(&a_full[s], TC_A_BYTES);
                         tma2d(Asm + (size_t)s * TC_A_BYTES, &amap, c * 32, (int)(L0 + (long long)blk * 128), &a_full[s]);
                     }
@@ -244,50 +268,60 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
+        // One lane runs the whole loop: this warp's instruction latency is what feeds the tensor
+        // pipe (four MMAs of ~180 cycles per 16 KB stage), so the per-stage instruction count is
+        // kept minimal -- descriptors are base + increments, the stage ring is a counter.
         // idesc: D = f32, A = B = tf32, both K-major, N >> 3, M = 128 >> 4
-        const unsigned idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
-        unsigned ita = 0, blkc = 0;
-        for (unsigned t = 0;; t++) {
-            const int m = t & 1;
-            mb_wait(&m_full[m], (t >> 1) & 1);
-            const int flags = meta[m].flags, nblk = meta[m].nblk;
-            const int Nt = min(N, (meta[m].Qt + 31) / 32 * 32);  // MMA N: only the columns that hold queries
-            const unsigned idesc = idesc0 | ((unsigned)(Nt >> 3) << 17);
-            __syncwarp();
-            if (lane == 0) mb_arrive(&m_empty[m]);
-            if (flags) break;
-            mb_wait(&b_full, t & 1);
-            for (int blk = 0; blk < nblk; blk++, blkc++) {
-                const int buf = blkc & 1;
-                mb_wait(&t_empty[buf], ((blkc >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const unsigned d_tmem = tmem_base + buf * 256;
-                for (int c = 0; c < nchunk; c++, ita++) {
-                    const int s = ita % TC_ASTAGES;
-                    mb_wait(&a_full[s], (ita / TC_ASTAGES) & 1);
+        if (elect_one()) {
+            const unsigned idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
+            const unsigned long long adesc0 = umma_desc(s32(Asm)), bdesc0 = umma_desc(s32(Bsm));
+            const unsigned b_chunk_inc = (unsigned)(N * 128) >> 4;  // descriptor address units are 16 bytes
+            unsigned s = 0, a_phase = 0, blkc = 0;
+            for (unsigned t = 0;; t++) {
+                const int m = t & 1;
+                MB_WAIT(4, &m_full[m], (t >> 1) & 1);
+                const int flags = meta[m].flags, nblk = meta[m].nblk;
+                const int Nt = min(N, (meta[m].Qt + 31) / 32 * 32);  // MMA N: only the columns that hold queries
+                const unsigned idesc = idesc0 | ((unsigned)(Nt >> 3) << 17);
+                mb_arrive(&m_empty[m]);
+                if (flags) break;
+                MB_WAIT(5, &b_full, t & 1);
+                for (int blk = 0; blk < nblk; blk++, blkc++) {
+                    const int buf = blkc & 1;
+                    MB_WAIT(6, &t_empty[buf], ((blkc >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    if (lane == 0) {
-                        const unsigned a0 = s32(Asm + (size_t)s * TC_A_BYTES), b0 = s32(Bsm + (size_t)c * N * 128);
+                    const unsigned d_tmem = tmem_base + buf * 256;
+                    unsigned long long bdesc = bdesc0;
+                    for (int c = 0; c < nchunk; c++, bdesc += b_chunk_inc) {
+                        MB_WAIT(7, &a_full[s], a_phase);
+                        tc_fence_after();
+                        const unsigned long long adesc = adesc0 + s * (unsigned)(TC_A_BYTES >> 4);
 #pragma unroll
-                        for (int k = 0; k < 4; k++)  // K = 8 tf32 = 32 bytes per instruction
-                            umma_tf32(d_tmem, umma_desc(a0 + k * 32), umma_desc(b0 + k * 32), idesc, (c | k) != 0);
+                        for (int k = 0; k < 4; k++)  // K = 8 tf32 = 32 bytes (2 address units) per instruction
+                            umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (c | k) != 0);
                         umma_commit(&a_empty[s]);  // frees the A stage when these MMAs have read it
+                        if (++s == TC_ASTAGES) {
+                            s = 0;
+                            a_phase ^= 1;
+                        }
                     }
-                    __syncwarp();
+                    umma_commit(&t_full[buf]);
                 }
-                if (lane == 0) umma_commit(&t_full[buf]);
-                __syncwarp();
+                umma_commit(&b_empty);  // the tile's MMAs are done with the query block
             }
-            if (lane == 0) umma_commit(&b_empty);  // the tile's MMAs are done with the query block
-            __syncwarp();
         }
-    } else if (warp >= 2 && warp <= 5) {
+        __syncwarp();
+    } else if (warp >= 2 && warp <= 9) {
         // =========================== epilogue ===========================
+        // Two groups of four warps, one per accumulator buffer: group g drains the blocks whose
+        // running index is g (mod 2).  A lone warp per scheduler cannot hide its own TMEM / shared
+        // memory latencies; with two, one filters while the other waits.
         const int wq = warp & 3;  // TMEM lane quarter this warp may read
+        const int grp = (warp - 2) >> 2;
         unsigned blkc = 0;
         for (unsigned t = 0;; t++) {
             const int m = t & 1;
-            mb_wait(&m_full[m], (t >> 1) & 1);
+            MB_WAIT(8, &m_full[m], (t >> 1) & 1);
             const TileMeta* mt = &meta[m];
             if (mt->flags) {
                 __syncwarp();
@@ -299,12 +333,13 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
             const long long row0 = mt->row0;
             for (int blk = 0; blk < nblk; blk++, blkc++) {
                 const int buf = blkc & 1;
+                if (buf != grp) continue;
                 const int v = blk * 128 + wq * 32 + lane;
                 const bool valid = v < L;
                 const float nv = valid ? ta.vnorm[row0 + v] : 0.f;
                 const float snv = sqrtf(nv);
                 const float nvp = METRIC == METRIC_L2 ? nv * (1.f - ta.c2) : 0.f;
-                mb_wait(&t_full[buf], (blkc >> 1) & 1);
+                MB_WAIT(9, &t_full[buf], (blkc >> 1) & 1);
                 tc_fence_after();
                 for (int cg = 0; cg < ncg; cg++) {
                     unsigned r[32];
@@ -340,6 +375,14 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
             if (lane == 0) mb_arrive(&m_empty[m]);
         }
     }
+#ifdef TC_TIMING
+    if (blockIdx.x == 0 && lane == 0 && (warp <= 2 || warp == 6 || warp == 10)) {
+        const long long tot = clock64() - tc_t_begin;
+        printf("tc_filter warp %d: total %lld | m_empty %lld m_full %lld/%lld/%lld b_empty %lld a_empty %lld b_full %lld t_empty %lld a_full %lld t_full %lld\n",
+               warp, tot, tc_wait_acc[0], tc_wait_acc[1], tc_wait_acc[4], tc_wait_acc[8], tc_wait_acc[2], tc_wait_acc[3],
+               tc_wait_acc[5], tc_wait_acc[6], tc_wait_acc[7], tc_wait_acc[9]);
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
