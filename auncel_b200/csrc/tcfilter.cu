@@ -15,8 +15,8 @@
 //      reference's strict test.  Results are therefore bit-identical to the SIMT path; the
 //      tensor cores only decide what is worth computing exactly.
 // Warp roles (352 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected lane),
-// warps 2-9 epilogue (TMEM -> registers -> filter; warps 2-5 drain accumulator 0, warps 6-9
-// accumulator 1), warp 10 tile scheduler (claims and decodes the next tile and its per-query
+// warps 2-9 epilogue (TMEM -> registers -> filter; warps 2-5 take the even 32-column chunks of
+// each accumulator, warps 6-9 the odd ones), warp 10 tile scheduler (claims and decodes the next tile and its per-query
 // constants while the current one streams).  TMEM: 2 x 256 fp32 columns, double buffered so the
 // MMAs of block b+1 overlap the filter of block b.
 #include <cuda.h>
@@ -156,7 +156,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
         mb_init(&b_empty, 1);
         for (int i = 0; i < 2; i++) {
             mb_init(&t_full[i], 1);
-            mb_init(&t_empty[i], 4);
+            mb_init(&t_empty[i], 8);
             mb_init(&m_full[i], 1);
             mb_init(&m_empty[i], 10);  // TMA warp + MMA warp + 8 epilogue warps
         }
@@ -313,9 +313,10 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
         __syncwarp();
     } else if (warp >= 2 && warp <= 9) {
         // =========================== epilogue ===========================
-        // Two groups of four warps, one per accumulator buffer: group g drains the blocks whose
-        // running index is g (mod 2).  A lone warp per scheduler cannot hide its own TMEM / shared
-        // memory latencies; with two, one filters while the other waits.
+        // Two groups of four warps; both drain every accumulator, group g taking the 32-column
+        // chunks g, g+2, ...  The filter of a block must finish within the MMA time of the next
+        // one or the MMA warp stalls on t_empty; eight warps halve it and give every scheduler two
+        // epilogue warps to hide TMEM / shared-memory latencies.
         const int wq = warp & 3;  // TMEM lane quarter this warp may read
         const int grp = (warp - 2) >> 2;
         unsigned blkc = 0;
@@ -333,7 +334,6 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
             const long long row0 = mt->row0;
             for (int blk = 0; blk < nblk; blk++, blkc++) {
                 const int buf = blkc & 1;
-                if (buf != grp) continue;
                 const int v = blk * 128 + wq * 32 + lane;
                 const bool valid = v < L;
                 const float nv = valid ? ta.vnorm[row0 + v] : 0.f;
@@ -341,7 +341,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                 const float nvp = METRIC == METRIC_L2 ? nv * (1.f - ta.c2) : 0.f;
                 MB_WAIT(9, &t_full[buf], (blkc >> 1) & 1);
                 tc_fence_after();
-                for (int cg = 0; cg < ncg; cg++) {
+                for (int cg = grp; cg < ncg; cg += 2) {
                     unsigned r[32];
                     tmem_ld32(tmem_base + ((unsigned)(wq * 32) << 16) + buf * 256 + cg * 32, r);
                     unsigned hits = 0;
