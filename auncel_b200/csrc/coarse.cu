@@ -191,6 +191,110 @@ rank_rows_kernel(int metric, const float* __restrict__ dis, long nlist, int P, f
     if (threadIdx.x == 0) tie0[q] = s_tie;
 }
 
+// The same ranking for P >= 256 with E keys per thread held in registers: compare-exchange
+// distances below E stay in registers, distances below 32 E go through warp shuffles, only the
+// longer ones through shared memory (10 of the 78 network stages at P = 4096).  Shared-memory
+// element i lives at i ^ (((i >> 4) & 7) << 1): both the blocked (thread t owns [tE, tE+E)) and
+// the strided access patterns are then bank-conflict free.
+__device__ __forceinline__ int rr_sw(int i) { return i ^ (((i >> 4) & 7) << 1); }
+
+template <int E>
+__global__ void __launch_bounds__(1024)
+rank_rows_reg_kernel(int metric, const float* __restrict__ dis, long nlist, int P, float* __restrict__ out_dis,
+                     int* __restrict__ out_keys, int* __restrict__ tie0) {
+    extern __shared__ __align__(16) unsigned long long skey[];
+    __shared__ int s_tie;
+    const int t = threadIdx.x, T = blockDim.x, lane = t & 31;
+    if (t == 0) s_tie = 0x7fffffff;
+    const long q = blockIdx.x;
+    const float* row = dis + q * nlist;
+    const int base = t * E;
+    unsigned long long e[E];
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+        const int i = base + r;
+        unsigned long long key = ~0ull;
+        if (i < nlist) {
+            uint32_t o = f2ord(row[i]);
+            if (metric == METRIC_IP) o = ~o;
+            key = ((unsigned long long)o << 32) | (unsigned)i;
+        }
+        e[r] = key;
+    }
+    for (int size = 2; size <= P; size <<= 1) {
+        int stride = size >> 1;
+        if (stride >= 32 * E) {
+            // long distances: through shared memory, E/2 pairs per thread and stage
+#pragma unroll
+            for (int r = 0; r < E; r += 2)
+                *reinterpret_cast<ulonglong2*>(&skey[rr_sw(base + r)]) = make_ulonglong2(e[r], e[r + 1]);
+            __syncthreads();
+            for (; stride >= 32 * E; stride >>= 1) {
+#pragma unroll
+                for (int j = 0; j < E / 2; j++) {
+                    const int p = t + j * T;
+                    const int lo = 2 * p - (p & (stride - 1)), hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    const unsigned long long a = skey[rr_sw(lo)], b = skey[rr_sw(hi)];
+                    if ((a > b) == up) {
+                        skey[rr_sw(lo)] = b;
+                        skey[rr_sw(hi)] = a;
+                    }
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int r = 0; r < E; r += 2) {
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&skey[rr_sw(base + r)]);
+                e[r] = v.x;
+                e[r + 1] = v.y;
+            }
+        }
+        for (; stride >= E; stride >>= 1) {  // partner element lives in lane ^ (stride / E), same register
+            const int lm = stride / E;
+            const bool keep_min = ((lane & lm) == 0) == ((base & size) == 0);
+#pragma unroll
+            for (int r = 0; r < E; r++) {
+                const unsigned lo32 = __shfl_xor_sync(0xffffffffu, (unsigned)e[r], lm);
+                const unsigned hi32 = __shfl_xor_sync(0xffffffffu, (unsigned)(e[r] >> 32), lm);
+                const unsigned long long o = ((unsigned long long)hi32 << 32) | lo32;
+                e[r] = keep_min ? (o < e[r] ? o : e[r]) : (o > e[r] ? o : e[r]);
+            }
+        }
+#pragma unroll
+        for (int st = E / 2; st > 0; st >>= 1) {
+            if (st <= stride) {
+#pragma unroll
+                for (int r = 0; r < E; r++) {
+                    if ((r & st) == 0) {
+                        const bool up = ((base + r) & size) == 0;
+                        const unsigned long long a = e[r], b = e[r | st];
+                        if ((a > b) == up) {
+                            e[r] = b;
+                            e[r | st] = a;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < E; r += 2)
+        *reinterpret_cast<ulonglong2*>(&skey[rr_sw(base + r)]) = make_ulonglong2(e[r], e[r + 1]);
+    __syncthreads();
+    for (int i = t; i < nlist; i += T) {
+        const unsigned long long key = skey[rr_sw(i)];
+        uint32_t o = (uint32_t)(key >> 32);
+        if (metric == METRIC_IP) o = ~o;
+        out_dis[q * nlist + i] = ord2f(o);
+        out_keys[q * nlist + i] = (int)(key & 0xffffffffu);
+        if (i + 1 < nlist && (uint32_t)(skey[rr_sw(i + 1)] >> 32) == (uint32_t)(key >> 32)) atomicMin(&s_tie, i);
+    }
+    __syncthreads();
+    if (t == 0) tie0[q] = s_tie;
+}
+
 // ---------------------------------------------------------------------------------
 // Exact tie order.  IndexFlat::search ranks centroids with a binary heap of size k (= nprobe;
 // nlist in Auncel mode): knn_L2sqr_sse / knn_inner_product_sse (utils.cpp:417-490) push every
@@ -566,6 +670,15 @@ void launch_rank_rows(int metric, const float* dis, long nq, long nlist, float* 
     while (P < nlist) P <<= 1;
     size_t smem = (size_t)P * sizeof(unsigned long long);
     AUNCEL_CHECK(smem <= 220 * 1024, "nlist too large for the in-smem centroid ranking");
+    if (P >= 256) {  // register / shuffle / shared-memory hybrid
+        auto kern = P <= 8192 ? rank_rows_reg_kernel<8> : rank_rows_reg_kernel<16>;
+        const int threads = P <= 8192 ? P / 8 : P / 16;
+        AUNCEL_CHECK(threads <= 1024, "nlist too large for the in-smem centroid ranking");
+        if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)nq, threads, smem, s>>>(metric, dis, nlist, P, out_dis, out_keys, tie0);
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     if (smem > 48 * 1024)
         CUDA_CHECK(cudaFuncSetAttribute(rank_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int threads = std::max(32, std::min(1024, P / 2));

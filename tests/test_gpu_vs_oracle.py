@@ -253,3 +253,25 @@ def test_cpp_api_mirror_demo():
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "DEMO OK" in r.stdout
     assert "Error bound is guaranteed" in r.stdout
+
+
+@pytest.mark.parametrize("metric,nlist", [(O.L2, 256), (O.L2, 300), (O.IP, 1000), (O.L2, 1024), (O.L2, 2048),
+                                          (O.IP, 4096), (O.L2, 5000), (O.L2, 9000)])
+def test_coarse_full_ranking_large_nlist(metric, nlist):
+    """Full centroid ranking through the register/shuffle/shared-memory sort (coarse.cu
+    rank_rows_reg_kernel, P >= 256) and the pipelined tie replay, incl. heap sizes that are not a
+    power of two; quantised coordinates force plenty of equal distances."""
+    d = 6
+    rng = np.random.RandomState(nlist)
+    cent = (rng.randint(-6, 7, size=(nlist, d)) / 4.0).astype(np.float32)
+    cent[: nlist // 2] += (rng.rand(nlist // 2, d) * 1e-3).astype(np.float32)  # half of them distinct
+    xq = (rng.randint(-6, 7, size=(9, d)) / 4.0).astype(np.float32)
+    orc = O.OracleIndex(d, nlist, metric)
+    orc.centroids = cent
+    ix = ab.IndexIVFFlat(d, nlist, metric)
+    ix.set_centroids(cent, compute_interdis=False)
+    for nprobe in (nlist, max(1, nlist // 3)):
+        dis, keys = ix.coarse_search(xq, nprobe)
+        odis, okeys = orc.coarse(xq, nprobe)
+        assert np.array_equal(dis, odis), (nlist, nprobe)
+        assert np.array_equal(keys, okeys), (nlist, nprobe)
