@@ -483,7 +483,9 @@ void IvfIndex::search(const QueryBatch& qb) {
         S = std::max(1L, std::min<long>(S, 32));
         // narrow tiles (8 queries, rows split over warps) when lists are probed by few queries
         const double avg_q = (double)n_active * w / (double)std::min<long>(nlist, (long)n_active * w);
-        int nsub = avg_q <= 10.0 ? 4 : avg_q <= 24.0 ? 2 : 1;
+        static const double nsub_t4 = getenv("AUNCEL_NSUB_T4") ? atof(getenv("AUNCEL_NSUB_T4")) : 10.0;
+        static const double nsub_t2 = getenv("AUNCEL_NSUB_T2") ? atof(getenv("AUNCEL_NSUB_T2")) : 24.0;
+        int nsub = avg_q <= nsub_t4 ? 4 : avg_q <= nsub_t2 ? 2 : 1;
         while (nsub > 1 && (size_t)n_active * w * nsub * K > pool_entries) nsub >>= 1;
         while (S > 1 && (size_t)n_active * w * S * nsub * K > pool_entries) S--;
         rp.qt = SCAN_QT / nsub;

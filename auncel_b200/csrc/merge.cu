@@ -170,13 +170,14 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
         }
         for (int seg = 0; seg < nseg; seg++) {
             const long slot = ((long)a * rp.w + p_rel) * nseg + seg;
-            const int c = min(rp.slot_cnt[slot], K);
+            const int raw_cnt = rp.slot_cnt[slot];
+            const int c = min(raw_cnt & ~SLOT_SORTED, K);
             if (c == 0) continue;
             const int rcnt_before = rcnt;
             const float kth_before = (qk_i >= 1 && rcnt >= qk_i) ? sm.Rd[qk_i - 1] : neut;
-            if (rp.unsorted) {
-                // tensor-core rounds: rerank_kernel appended survivors in arrival order; order them
-                // by (distance, offset) like the scan kernel does, in place
+            if (!(raw_cnt & SLOT_SORTED)) {
+                // rerank_kernel (tensor-core rounds) appends survivors in arrival order and the exact
+                // scan hands over short lists as they are: order them by (distance, offset), in place
                 if (c <= 32) {
                     unsigned long long kk = ~0ull;
                     if (lane < c) {

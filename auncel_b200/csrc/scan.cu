@@ -438,9 +438,22 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
     unsigned tcount = 0;
     int tslot = 0;
 
+#ifdef SCAN_TIMING
+    long long tm[5] = {0, 0, 0, 0, 0}, tm_prev = clock64();  // wait, header, distance, filter, write-out
+#define SCAN_TICK(k)                      \
+    do {                                  \
+        const long long now_ = clock64(); \
+        tm[k] += now_ - tm_prev;          \
+        tm_prev = now_;                   \
+    } while (0)
+#else
+#define SCAN_TICK(k)
+#endif
     for (unsigned it = 0;; it++) {
         const int s = it % STAGES;
+        SCAN_TICK(4);
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        SCAN_TICK(0);
         const unsigned char* st = smem + (size_t)s * STAGE_BYTES;
         const StageHdr* h = reinterpret_cast<const StageHdr*>(st + VT_BYTES + QT_BYTES);
         const int4 h0 = *reinterpret_cast<const int4*>(&h->flags);  // flags, first, last_chunk, last_iter
@@ -470,6 +483,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
             for (int i = 0; i < 4; i++) slot[i] = h->slot[min(q0 + i, SCAN_QT - 1)];
         }
 
+        SCAN_TICK(1);
 #ifdef SCAN_EXP_NODIST
         if (false) {
 #else
@@ -485,6 +499,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
                 default: dist_chunk<METRIC, TV, 4>(acc, sq, sv, nkc, xr); break;
             }
         }
+        SCAN_TICK(2);
         // the stage's data and header are consumed: hand the slot back to the producer
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -524,6 +539,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
                 }
             }
         }
+        SCAN_TICK(3);
         if (has_q && last_iter) {
             // ---- per-(query, segment[, row subset]) result: sorted, at most K candidates
 #pragma unroll
@@ -539,21 +555,30 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
                             rp.cand_d[sl * K + lane] = key_dist<METRIC>(key);
                             rp.cand_off[sl * K + lane] = (unsigned)(key & 0xffffffffu);
                         }
-                        if (lane == 0) rp.slot_cnt[sl] = c;
+                        if (lane == 0) rp.slot_cnt[sl] = c | SLOT_SORTED;
                     } else {
-                        compact<METRIC>(buf, cnt[i], tau[i], K, lane);
+                        // up to K candidates go out as they are: sorting them here would stall the
+                        // whole CTA's stage ring behind one warp, merge_check orders them instead
+                        const bool sorted = cnt[i] > K;
+                        if (sorted) compact<METRIC>(buf, cnt[i], tau[i], K, lane);
                         for (int t = lane; t < cnt[i]; t += 32) {
                             unsigned long long key = buf[t];
                             rp.cand_d[sl * K + t] = key_dist<METRIC>(key);
                             rp.cand_off[sl * K + t] = (unsigned)(key & 0xffffffffu);
                         }
-                        if (lane == 0) rp.slot_cnt[sl] = cnt[i];
+                        if (lane == 0) rp.slot_cnt[sl] = cnt[i] | (sorted ? SLOT_SORTED : 0);
                     }
                     __syncwarp();
                 }
             }
         }
     }
+#ifdef SCAN_TIMING
+    SCAN_TICK(4);
+    if (blockIdx.x == 0 && lane == 0)
+        printf("scan<%d> warp %d: wait %lld header %lld distance %lld filter %lld writeout %lld\n", RSPLIT, warp, tm[0],
+               tm[1], tm[2], tm[3], tm[4]);
+#endif
 }
 
 // -------------------------------------------------------------------------

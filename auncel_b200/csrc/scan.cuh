@@ -41,6 +41,10 @@ struct QState {
     }
 };
 
+// slot_cnt[slot] = number of candidates | SLOT_SORTED when they are ordered by (distance, offset);
+// unordered slots (tensor-core rerank, short exact-scan results) are ordered by merge_check
+constexpr int SLOT_SORTED = 1 << 30;
+
 struct RoundParams {
     // index
     const float* codes;
@@ -61,7 +65,7 @@ struct RoundParams {
     int r0, w, S;
     int qt;               // queries per scan tile this round: 32 / nsub
     int nsub;             // sub-slots per (query, rank, segment) = row subsets of the scan tile (1, 2 or 4)
-    int unsorted;         // 1: slots were filled by rerank_kernel in arrival order (tensor-core rounds)
+    int unsorted;         // (logging)  1: slots were filled by rerank_kernel in arrival order (tensor-core rounds)
     int* pair_flag;       // tensor-core rounds: per slot, 1 = overflowed -> redo this pair with the exact scan
     int filtered;         // plan only the flagged pairs
     // plan
