@@ -27,9 +27,31 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+
+# stdout carries exactly one JSON line.  The unmodified reference (oracle/_ref) prints progress with
+# printf; file descriptor 1 is therefore pointed at stderr and the JSON goes out through a private copy.
+_JSON_OUT = None
+
+
+def emit(obj):
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        _JSON_OUT = sys.stdout
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
+
+def isolate_stdout():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 sys.path.insert(0, ROOT)
 
 QUERY_TOPK = 10
+# dram__bytes_read.sum + dram__bytes_write.sum per tc_filter launch, mean of the three launches of one
+# default step under ncu (profiles/r01_tc_traffic.txt)
+TC_TRAFFIC_PER_LAUNCH = 6.51e9
 MAX_TOPK = 100
 # (multipler, std_m) per error bound: Auncel/hyperparameter.txt lines 6 / 7 are the authors'
 # SIFT10M k=10 settings for eb=0.1 / 0.05 (eval/run.sh:13-15); eb=0.2 reuses line 6.
@@ -251,24 +273,36 @@ def run_ours(a):
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * sm_mhz * 1e6 / 1e12  # FP32 lane-ops/s at the measured clock (no FMA on the exact path)
     flop_per_dis = 3 * d if metric == 1 else 2 * d
-    # DRAM bytes of one tensor-core launch, from the committed ncu capture (profiles/r01_tc_filter_ncu.txt):
-    # every launch streams the list arena once (plus the gathered queries)
+    # DRAM bytes per tensor-core launch: measured with ncu on this very command (dram__bytes_read+write of
+    # the three tc_filter launches of a step, profiles/r01_scan_tc_ncu_v3.txt / r01_tc_traffic.txt)
+    tf32_peak = None
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        tf32_peak = mp.get("bf16_tflops", 0) / 2.0 or None  # tf32 runs at half the measured dense bf16 rate
+    except Exception:
+        pass
+    tc_tflops = tc_ndis * 2 * d / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else None
     roofline = {
         "kernel": "tc_filter_kernel", "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
         "achieved": tc_ndis * 4 * d / (tc_ms / 1e3) / 1e9 if tc_ms > 0 else None,
         "frac": tc_ndis * 4 * d / (tc_ms / 1e3) / 1e9 / peak if tc_ms > 0 else None,
-        "traffic": 5.73e9 if (a.nb == 10_000_000 and d == 128) else None,
+        "traffic": TC_TRAFFIC_PER_LAUNCH if (a.nb == 10_000_000 and d == 128 and a.nlist == 4096) else None,
         "per_launch": {"alg_bytes": tc_ndis * 4 * d / max(tc_launches, 1), "ms": tc_ms / max(tc_launches, 1),
                        "launches_per_step": tc_launches},
         "dram": {"note": "compulsory traffic = bytes of the distinct lists each launch touches (counted by the plan "
                          "kernel); staged = bytes TMA moved into shared memory (one list pass per 256-query tile). "
-                         "ncu on a full-arena launch: 5.73 GB read in 1.63 ms (profiles/r01_tc_filter_ncu.txt)",
+                         "ncu per launch (profiles/r01_scan_tc_ncu_v3.txt): launches with ~1 query tile per list run "
+                         "at 6.76 TB/s DRAM (103 % of the measured copy peak); launches with 3-4 query tiles per "
+                         "list are bound by the tf32 MMA rate (tensor pipe 60 % active, 3.7 TB/s DRAM, 1.9x the "
+                         "arena because L2 keeps only part of a list between its query tiles)",
                  "compulsory_bytes_per_step": float(np.mean(tcs["tc_uniq"])) * 4 * d,
                  "staged_bytes_per_step": float(np.mean(tcs["tc_staged"])) * 4 * d,
                  "compulsory_gbs": float(np.mean(tcs["tc_uniq"])) * 4 * d / (tc_ms / 1e3) / 1e9 if tc_ms > 0 else None,
                  "staged_gbs": float(np.mean(tcs["tc_staged"])) * 4 * d / (tc_ms / 1e3) / 1e9 if tc_ms > 0 else None,
                  "compulsory_frac_of_peak": float(np.mean(tcs["tc_uniq"])) * 4 * d / (tc_ms / 1e3) / 1e9 / peak if tc_ms > 0 else None},
-        "tensor": {"achieved_tflops_tf32": tc_ndis * 2 * d / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else None},
+        "tensor": {"achieved_tflops_tf32": tc_tflops, "peak_tflops_tf32": tf32_peak,
+                   "frac": tc_tflops / tf32_peak if (tc_tflops and tf32_peak) else None,
+                   "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2"},
         "note": "algorithmic bytes = ndis*4d as the reference streams them (one list pass per probing query); one "
                 "staged tile serves up to 256 queries, so achieved/peak > 1 is reuse -- the HBM-level figure is "
                 "`dram` (each launch reads the arena about once)",
@@ -296,7 +330,7 @@ def run_ours(a):
     if rank == 0 and world == 1 and not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline(a, S, np_eb, D_eb)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -364,7 +398,7 @@ def run_reference(a):
         return
     from oracle import oracle as O
     if not O.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libauncel_ref.so not present"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libauncel_ref.so not present"})
         return
     import torch
     torch.cuda.set_device(0)
@@ -383,7 +417,7 @@ def run_reference(a):
     R.close()
     t = float(np.mean(times))
     v = nsample / t
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "QPS at fixed error bound & recall@10, 10M x 128 SIFT-shape", "value": v,
         "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -393,11 +427,12 @@ def run_reference(a):
         "cpu_baseline": {"value": v, "unit": "queries/s", "cores": cores, "kind": "reference",
                          "sample": f"{nsample} test queries per step, batched Error_sys::search on {cores} threads"},
         "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}), flush=True)
+        "gpu_launches": 0})
 
 
 if __name__ == "__main__":
     args = parse()
+    isolate_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
