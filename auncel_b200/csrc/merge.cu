@@ -109,6 +109,7 @@ void launch_set_online(int metric, long nlist, long n, const float* cdis, const 
 
 // --------------------------------------------------------------------------- merge + check
 constexpr int MC_WARPS = 4;
+constexpr int MC_INSERT_MAX = 8;  // slots with at most this many candidates are merged by insertion
 
 template <int KP>
 struct MergeSmem {
@@ -175,6 +176,79 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
             if (c == 0) continue;
             const int rcnt_before = rcnt;
             const float kth_before = (qk_i >= 1 && rcnt >= qk_i) ? sm.Rd[qk_i - 1] : neut;
+            if (c <= MC_INSERT_MAX) {
+                // A handful of candidates (the usual case after the tensor-core filter): insert them one
+                // by one into the sorted top-k instead of a 2*KP bitonic merge.  A candidate goes behind
+                // every held value <= it, like the (value, arrival) order of the merge below.
+                unsigned long long kk = ~0ull;
+                if (lane < c) {
+                    uint32_t o = f2ord(rp.cand_d[slot * K + lane]);
+                    if (metric == METRIC_IP) o = ~o;
+                    kk = ((unsigned long long)o << 32) | rp.cand_off[slot * K + lane];
+                }
+                if (!(raw_cnt & SLOT_SORTED)) {
+#pragma unroll
+                    for (int k2 = 2; k2 <= MC_INSERT_MAX; k2 <<= 1)
+#pragma unroll
+                        for (int j = k2 >> 1; j > 0; j >>= 1) {
+                            unsigned long long other = __shfl_xor_sync(0xffffffffu, kk, j);
+                            bool up = ((lane & k2) == 0), lower = ((lane & j) == 0);
+                            unsigned long long mn = kk < other ? kk : other, mx = kk < other ? other : kk;
+                            kk = (lower == up) ? mn : mx;
+                        }
+                }
+                constexpr int EPL = (KP + 31) / 32;
+                float best = 0.f;
+                for (int t = 0; t < c; t++) {
+                    const unsigned long long ck = __shfl_sync(0xffffffffu, kk, t);
+                    const uint32_t co = (uint32_t)(ck >> 32);
+                    const float cd = ord2f(metric == METRIC_IP ? ~co : co);
+                    if (t == 0) best = cd;
+                    int pos = 0;
+#pragma unroll
+                    for (int j = 0; j < EPL; j++) {
+                        const int i = lane + 32 * j;
+                        bool le = false;
+                        if (i < rcnt) {
+                            uint32_t o = f2ord(sm.Rd[i]);
+                            if (metric == METRIC_IP) o = ~o;
+                            le = o <= co;
+                        }
+                        pos += __popc(__ballot_sync(0xffffffffu, le));
+                    }
+                    if (pos >= K) break;  // the heap is full of values <= this one; the rest is no better
+                    float nd[EPL];
+                    unsigned long long nc[EPL];
+#pragma unroll
+                    for (int j = 0; j < EPL; j++) {
+                        const int i = lane + 32 * j;
+                        if (i < KP) {
+                            const int src = i > pos ? i - 1 : i;
+                            nd[j] = sm.Rd[src];
+                            nc[j] = sm.code[cur][src];
+                            if (i == pos) {
+                                nd[j] = cd;
+                                nc[j] = ((unsigned long long)(unsigned)(stage - 1) << 32) | (unsigned)(ck & 0xffffffffu);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    rcnt = min(K, rcnt + 1);
+#pragma unroll
+                    for (int j = 0; j < EPL; j++) {
+                        const int i = lane + 32 * j;
+                        if (i < KP && i >= pos && i < rcnt) {
+                            sm.Rd[i] = nd[j];
+                            sm.code[cur][i] = nc[j];
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (tp.mode == 1 && qk_i >= 1) {
+                    if (rcnt_before < qk_i || (metric == METRIC_L2 ? best < kth_before : best > kth_before)) topq_dirty = 1;
+                }
+                continue;
+            }
             if (!(raw_cnt & SLOT_SORTED)) {
                 // rerank_kernel (tensor-core rounds) appends survivors in arrival order and the exact
                 // scan hands over short lists as they are: order them by (distance, offset), in place
