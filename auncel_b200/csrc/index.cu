@@ -486,11 +486,15 @@ void IvfIndex::search(const QueryBatch& qb) {
         static const double nsub_t4 = getenv("AUNCEL_NSUB_T4") ? atof(getenv("AUNCEL_NSUB_T4")) : 10.0;
         static const double nsub_t2 = getenv("AUNCEL_NSUB_T2") ? atof(getenv("AUNCEL_NSUB_T2")) : 24.0;
         int nsub = avg_q <= nsub_t4 ? 4 : avg_q <= nsub_t2 ? 2 : 1;
+        // a handful of queries: the per-query merge of S*nsub partial results per list is the latency,
+        // not the scan -- do not split rows over warps as well
+        if (n_active <= 64) nsub = 1;
         while (nsub > 1 && (size_t)n_active * w * nsub * K > pool_entries) nsub >>= 1;
         while (S > 1 && (size_t)n_active * w * S * nsub * K > pool_entries) S--;
         rp.qt = SCAN_QT / nsub;
         rp.nsub = nsub;
         rp.unsorted = 0;
+        rp.defer_sort = n_active >= 1024 ? 1 : 0;  // few queries: one merge warp per query would sort serially
         rp.filtered = 0;
         rp.pair_flag = nullptr;
         // tensor-core filter round: (nearly) every remaining query already holds K results, so only

@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
                     } else {
                         // up to K candidates go out as they are: sorting them here would stall the
                         // whole CTA's stage ring behind one warp, merge_check orders them instead
-                        const bool sorted = cnt[i] > K;
+                        const bool sorted = cnt[i] > K || !rp.defer_sort;
                         if (sorted) compact<METRIC>(buf, cnt[i], tau[i], K, lane);
                         for (int t = lane; t < cnt[i]; t += 32) {
                             unsigned long long key = buf[t];

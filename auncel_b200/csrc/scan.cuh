@@ -65,6 +65,7 @@ struct RoundParams {
     int r0, w, S;
     int qt;               // queries per scan tile this round: 32 / nsub
     int nsub;             // sub-slots per (query, rank, segment) = row subsets of the scan tile (1, 2 or 4)
+    int defer_sort;       // 1: the exact scan may hand over <= K candidates unsorted (many queries: merge_check has the warps)
     int unsorted;         // (logging)  1: slots were filled by rerank_kernel in arrival order (tensor-core rounds)
     int* pair_flag;       // tensor-core rounds: per slot, 1 = overflowed -> redo this pair with the exact scan
     int filtered;         // plan only the flagged pairs
