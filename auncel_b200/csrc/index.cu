@@ -458,7 +458,8 @@ void IvfIndex::search(const QueryBatch& qb) {
         // doubles its window (1,1,2,4,...) so undecided queries never speculate far past their
         // stop stage (with multipler >= 2 every speculative list is needed anyway).
         long w_cap = (long)(pool_budget_bytes / ((size_t)n_active * ((size_t)K * 8 + (size_t)dpad * 4)));
-        w_cap = std::max(1L, std::min<long>(w_cap, 1024));
+        static const long w_hard = getenv("AUNCEL_WMAX") ? atol(getenv("AUNCEL_WMAX")) : 1024;
+        w_cap = std::max(1L, std::min<long>(w_cap, w_hard));
         long w = max_stage - r0;
         if (qb.mode == 1 && !qb.overhead_profile) {
             // few queries: start with a wider window -- speculative lists cost little HBM time,
@@ -471,6 +472,12 @@ void IvfIndex::search(const QueryBatch& qb) {
             double g = std::min<double>(std::max<double>(multipler, 2.0), 8.0);
             if (const char* e = getenv("AUNCEL_GROWTH")) g = std::max(2.0, atof(e));
             w = std::min<long>(w, std::max<long>(w0, (long)(r0 * (g - 1.0))));
+            // the round after the first list still runs on the exact FP32 scan (loose thresholds would
+            // overflow the tensor-core filter's per-pair slots): keep it short, the filter takes over next
+            // (measured: 3 lists at d = 128, no cap at d = 96 where the exact scan is cheaper per pair)
+            static const long w1_env = getenv("AUNCEL_W1") ? atol(getenv("AUNCEL_W1")) : -1;
+            const long w1_cap = w1_env >= 0 ? w1_env : (dpad >= 128 ? 3 : 0);
+            if (w1_cap > 0 && stats.rounds == 1 && n >= 2048) w = std::min<long>(w, w1_cap);
         } else if ((long)n_active * max_stage >= 4096 && max_stage > 8) {
             // plain / calibration search: a few narrow rounds first, so that the bulk of the
             // lists is scanned against a tight threshold (cheap selection)
