@@ -49,9 +49,9 @@ def isolate_stdout():
 sys.path.insert(0, ROOT)
 
 QUERY_TOPK = 10
-# dram__bytes_read.sum + dram__bytes_write.sum per tc_filter launch, mean of the three launches of one
-# default step under ncu (profiles/r01_tc_traffic.txt)
-TC_TRAFFIC_PER_LAUNCH = 6.51e9
+# dram__bytes_read.sum + dram__bytes_write.sum per tc_filter launch, mean of the four launches of one
+# default step under ncu (profiles/r01_tc_traffic.txt: 5.48 + 7.26 + 5.73 + 3.16 GB in 4.42 ms)
+TC_TRAFFIC_PER_LAUNCH = 5.40e9
 MAX_TOPK = 100
 # (multipler, std_m) per error bound: Auncel/hyperparameter.txt lines 6 / 7 are the authors'
 # SIFT10M k=10 settings for eb=0.1 / 0.05 (eval/run.sh:13-15); eb=0.2 reuses line 6.
@@ -274,7 +274,7 @@ def run_ours(a):
     fp32_peak = 148 * 128 * sm_mhz * 1e6 / 1e12  # FP32 lane-ops/s at the measured clock (no FMA on the exact path)
     flop_per_dis = 3 * d if metric == 1 else 2 * d
     # DRAM bytes per tensor-core launch: measured with ncu on this very command (dram__bytes_read+write of
-    # the three tc_filter launches of a step, profiles/r01_scan_tc_ncu_v3.txt / r01_tc_traffic.txt)
+    # the four tc_filter launches of a step, profiles/r01_scan_tc_ncu_v3.txt / r01_tc_traffic.txt)
     tf32_peak = None
     try:
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
