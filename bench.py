@@ -240,7 +240,12 @@ def run_ours(a):
 
     ms_step = float(np.mean(dev_ms))
     e2e_step = float(np.mean(e2e_s))
+    per_rank_ms = [ms_step]
     if world > 1:
+        mine = torch.tensor([ms_step], device=dev, dtype=torch.float64)
+        allr = torch.empty(world, device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank_ms = [float(v) for v in allr.cpu()]
         t = torch.tensor([ms_step, e2e_step], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step, e2e_step = float(t[0]), float(t[1])
@@ -326,6 +331,7 @@ def run_ours(a):
                 "d2h_bytes_per_step": n * MAX_TOPK * 12 + n * 8, "ms_per_step": 1e3 * e2e_step},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "quality": quality,
         "error_bounds": other, "setup_s": S["setup_s"], "timed_region_s": region_s,
+        "per_rank_ms_per_step": per_rank_ms,
     }
     if rank == 0 and world == 1 and not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline(a, S, np_eb, D_eb)
