@@ -124,9 +124,14 @@ template <int KP>
 __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams rp, TuneParams tp) {
     __shared__ MergeSmem<KP> sm_all[MC_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a = blockIdx.x * MC_WARPS + warp;
-    if (a >= rp.n_active) return;
     MergeSmem<KP>& sm = sm_all[warp];
+    // persistent warps: queries are handed out through a counter, so a warp that drew a short
+    // (decided, nothing to merge) query takes the next one instead of idling until the wave ends
+    for (;;) {  // (body not re-indented)
+    int a = 0;
+    if (lane == 0) a = atomicAdd(&rp.ctl[CTL_MERGE_NEXT], 1);
+    a = __shfl_sync(0xffffffffu, a, 0);
+    if (a >= rp.n_active) break;
     const int q = rp.active[a];
     const int K = rp.K, metric = rp.metric;
     const float neut = neutral(metric);
@@ -447,11 +452,22 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
         rp.st.tau[q] = rcnt == K ? sm.Rd[K - 1] : neut;
         if (err) atomicOr(&rp.ctl[CTL_ERR], err);
     }
+    __syncwarp();
+    }  // next query
 }
 
 void launch_merge_check(const RoundParams& rp, const TuneParams& tp, cudaStream_t s) {
     if (rp.n_active == 0) return;
     unsigned blocks = (unsigned)((rp.n_active + MC_WARPS - 1) / MC_WARPS);
+    static int resident_blocks = 0;
+    if (!resident_blocks) {
+        int dev = 0, sms = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        resident_blocks = sms * 8;
+    }
+    blocks = std::min<unsigned>(blocks, (unsigned)resident_blocks);
+    CUDA_CHECK(cudaMemsetAsync(rp.ctl + CTL_MERGE_NEXT, 0, sizeof(int), s));
     if (rp.K <= 16) merge_check_kernel<16><<<blocks, MC_WARPS * 32, 0, s>>>(rp, tp);
     else if (rp.K <= 32) merge_check_kernel<32><<<blocks, MC_WARPS * 32, 0, s>>>(rp, tp);
     else if (rp.K <= 64) merge_check_kernel<64><<<blocks, MC_WARPS * 32, 0, s>>>(rp, tp);
