@@ -454,9 +454,9 @@ void IvfIndex::search(const QueryBatch& qb) {
     const size_t pool_entries = std::max<size_t>(pool_budget_bytes / 8, (size_t)K);
     float scan_ms_total = 0.f;
     while (n_active > 0 && r0 < max_stage) {
-        // window: fixed/calibration scans as wide as the pool allows; the error-bounded search
-        // doubles its window (1,1,2,4,...) so undecided queries never speculate far past their
-        // stop stage (with multipler >= 2 every speculative list is needed anyway).
+        // window: fixed/calibration scans as wide as the pool allows; the error-bounded search grows
+        // its window with the rank already reached (see below), so undecided queries never speculate
+        // past what the reference itself would scan.
         long w_cap = (long)(pool_budget_bytes / ((size_t)n_active * ((size_t)K * 8 + (size_t)dpad * 4)));
         static const long w_hard = getenv("AUNCEL_WMAX") ? atol(getenv("AUNCEL_WMAX")) : 1024;
         w_cap = std::max(1L, std::min<long>(w_cap, w_hard));
