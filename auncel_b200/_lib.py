@@ -53,6 +53,7 @@ SYMBOLS = {
     "auncel_index_set_pool_budget": (C.c_int, [_h, C.c_size_t]),
     "auncel_index_set_option": (C.c_int, [_h, C.c_char_p, C.c_int]),
     "auncel_merge_tables": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, _f, _l, _l, _f, _l]),
+    "auncel_heap_entry_table": (C.c_int, [C.c_int64, C.POINTER(C.c_int32)]),
     "auncel_merge_tables_device": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "auncel_index_copy_subset_to": (C.c_int, [_h, _h, C.c_int, C.c_int64, C.c_int64]),

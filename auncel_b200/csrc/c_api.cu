@@ -725,4 +725,14 @@ int auncel_index_copy_subset_to(const AuncelIndex* idx, AuncelIndex* other, int 
     API_CATCH
 }
 
+int auncel_heap_entry_table(int64_t k, int32_t* entry_out) {
+    API_TRY
+    AUNCEL_CHECK(k >= 1 && k <= (1 << 24) && entry_out != nullptr, "heap_entry_table: bad arguments");
+    std::vector<int> e;
+    heap_entry_table((int)k, e);
+    std::copy(e.begin(), e.end(), entry_out);
+    return 0;
+    API_CATCH
+}
+
 }  // extern "C"

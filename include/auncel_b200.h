@@ -147,7 +147,7 @@ int auncel_index_get_stats(const AuncelIndex* idx, double* out24);
  * equal centroid distances */
 int auncel_index_set_option(AuncelIndex* idx, const char* name, int value);
 
-/* scratch budget for per-round candidate pools, bytes (default 1 GiB) */
+/* scratch budget for per-round candidate pools, bytes (default 4 GiB) */
 int auncel_index_set_pool_budget(AuncelIndex* idx, size_t bytes);
 
 /* merge_tables (IndexShards.cpp:44-105): k-way merge of nshard sorted (n x k) result tables
@@ -165,6 +165,15 @@ int auncel_merge_tables_device(int device, int metric, int64_t n, int64_t k, int
  * of ntotal).  This is how an index is split across GPUs (gpu/GpuAutoTune.cpp:201-220). */
 int auncel_index_copy_subset_to(const AuncelIndex* idx, AuncelIndex* other, int subset_type,
                                 int64_t a1, int64_t a2);
+
+/* Host-only helper behind the exact coarse tie order (csrc/coarse.cu heap_order_kernel): the
+ * structure of the reference's size-k result heap while it fills (knn_L2sqr_sse / heap_pop,
+ * utils.cpp:417-490, Heap.h:88-117).  entry_out[j], j < k = node where insertion j's sift-down meets
+ * its first data-dependent comparison; entry_out[k] = J, the number of leading insertions whose
+ * sift-downs run in subtrees disjoint from the root-to-slot-k path (done level-parallel on the GPU).
+ * entry_out must hold k + 1 ints.  Exposed so the CPU test-suite can check the table against a literal
+ * replay. */
+int auncel_heap_entry_table(int64_t k, int32_t* entry_out);
 
 #ifdef __cplusplus
 }
