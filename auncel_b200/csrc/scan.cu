@@ -117,13 +117,17 @@ __global__ void plan_fill_kernel(RoundParams rp) {
 // queries of the round, gathered in pair order: the query tile of a scan tile is then one
 // contiguous 32-row box that a single TMA load can fetch
 __global__ void gather_queries_kernel(RoundParams rp) {
-    long pos = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (pos >= rp.ctl[CTL_TOTAL_PAIRS]) return;
-    int a = (int)(rp.pairs[pos] >> 32);
-    const float4* src = reinterpret_cast<const float4*>(rp.xq + (long long)rp.active[a] * rp.dpad);
-    float4* dst = reinterpret_cast<float4*>(rp.xq_sorted + pos * rp.dpad);
-    for (int c = lane; c < rp.dpad / 4; c += 32) dst[c] = src[c];
+    // warp-stride loop over the pairs actually planned (a filtered plan keeps a small fraction of
+    // n_active * w, so the grid is sized for the hardware, not for the worst case)
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long total = rp.ctl[CTL_TOTAL_PAIRS];
+    for (long pos = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5; pos < total; pos += nwarps) {
+        const int a = (int)(rp.pairs[pos] >> 32);
+        const float4* src = reinterpret_cast<const float4*>(rp.xq + (long long)rp.active[a] * rp.dpad);
+        float4* dst = reinterpret_cast<float4*>(rp.xq_sorted + pos * rp.dpad);
+        for (int c = lane; c < rp.dpad / 4; c += 32) dst[c] = src[c];
+    }
 }
 
 void launch_plan(const RoundParams& rp, cudaStream_t s) {
@@ -134,7 +138,7 @@ void launch_plan(const RoundParams& rp, cudaStream_t s) {
     plan_count_kernel<<<blocks, 256, 0, s>>>(rp);
     plan_offsets_kernel<<<1, 1024, 0, s>>>(rp);
     plan_fill_kernel<<<blocks, 256, 0, s>>>(rp);
-    gather_queries_kernel<<<(unsigned)((tot * 32 + 255) / 256), 256, 0, s>>>(rp);
+    gather_queries_kernel<<<(unsigned)std::min<long>((tot * 32 + 255) / 256, 148L * 64), 256, 0, s>>>(rp);
     CUDA_CHECK(cudaGetLastError());
 }
 
