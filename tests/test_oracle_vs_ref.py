@@ -71,3 +71,58 @@ def test_shards_match_merge_tables():
     assert np.array_equal(D2, Dm) and np.array_equal(I2, Im)
     for r in subs + [full]:
         r.close()
+
+
+@pytest.mark.parametrize("metric,d,nb,k,qk,seed", [(O.L2, 12, 40000, 16, 4, 7), (O.L2, 40, 30000, 30, 10, 8),
+                                                    (O.IP, 20, 90000, 10, 3, 9)])
+def test_bounded_search_live(metric, d, nb, k, qk, seed):
+    """Calibration (Error_sys::sys_train -> traces) and error-bounded search of the restatement
+    against the unmodified reference run right here, on configurations the stored fixtures do not
+    hold: other dimensions, heap widths, query_topk and seeds.  Same flow as tests/golden/make_golden.py."""
+    O.RefIndex.set_blas_threshold(1 << 30)
+    nlist, ts, ses = 1024, 200, 100
+    norm = metric == O.IP
+    xb = synth.clustered(seed, nb, d, 400 if not norm else 2500, 0.32 if not norm else 0.45, normalize=norm)
+    xq = synth.clustered(seed + 100, ts + ses, d, 400 if not norm else 2500, 0.32 if not norm else 0.45, normalize=norm)
+    R = O.RefIndex(d, nlist, metric)
+    R.train(xb, niter=4)
+    cent = R.centroids()
+    R.add(xb)
+    ok = np.ones(len(xq), bool)
+    if norm:  # the reference throws when the first list holds < k vectors or a similarity exceeds 1
+        sizes = R.list_sizes()
+        dis, keys = R.coarse(xq, 1)
+        ok = (sizes[keys[:, 0]] >= k) & (dis[:, 0] <= 1.0)
+    cal = np.flatnonzero(ok[:ts])
+    tst = np.flatnonzero(ok[ts:]) + ts
+    cal, tst = cal[: len(cal) // 10 * 10], tst[: len(tst) // 10 * 10]
+    ts, ses = len(cal), len(tst)
+    assert ts >= 50 and ses >= 30
+    q = xq[np.concatenate([cal, tst])]
+    gD, gI = R.search_fixed(q, k, nlist)
+    R.es_create(gD, gI)
+    R.sys_train(ts, q)
+    ref_traces = R.traces()
+
+    orc = O.OracleIndex(d, nlist, metric)
+    orc.set_centroids(cent)
+    orc.add(xb)
+    assert np.array_equal(orc.assign(xb[:5000]), R.assign(xb[:5000]))
+    orc.calibrate(q[:ts], gD[:ts])
+    assert len(orc.traces) == len(ref_traces)
+    for a, b in zip(orc.traces, ref_traces):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    for mult, stdm, eb in [(1.0, 1.0, 0.1), (4.0, 3.0, 0.05), (7.9, 6.0, 0.2)]:
+        acc = np.full(ts + ses, 1 - eb, np.float32)
+        acc[::4] = 1 - eb / 3
+        R.set_queries(qk, ses, q, acc, mult, stdm, profile=True)
+        D, I = R.es_search(ts, ses, -1)
+        orc.multipler, orc.std_m = mult, stdm
+        D2, I2, mynp, trec = orc.search_bounded(q[ts:], k, qk, acc, gt_D=gD, offset=ts, profile=True)
+        assert orc.last_err == 0
+        assert np.array_equal(mynp[ts:], R.my_nprobe(ts, ses)), (mult, stdm, eb)
+        assert np.array_equal(D2, D) and np.array_equal(I2, I)
+        assert np.array_equal(trec[ts:], R.t_recalls(ts, ses))
+        R.clear_my_nprobe()
+    R.close()
