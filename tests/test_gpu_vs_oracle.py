@@ -275,3 +275,55 @@ def test_coarse_full_ranking_large_nlist(metric, nlist):
         odis, okeys = orc.coarse(xq, nprobe)
         assert np.array_equal(dis, odis), (nlist, nprobe)
         assert np.array_equal(keys, okeys), (nlist, nprobe)
+
+
+@pytest.mark.parametrize("metric,d,nb,k,qk,seed", [(O.L2, 12, 40000, 16, 4, 7), (O.L2, 40, 30000, 30, 10, 8),
+                                                    (O.IP, 20, 90000, 10, 3, 9)])
+def test_calibration_and_bounded_search_other_configs(metric, d, nb, k, qk, seed):
+    """Calibration traces and error-bounded search (D, my_nprobe) on configurations the fixtures do
+    not hold -- the ones tests/test_oracle_vs_ref.py::test_bounded_search_live pins the restatement on
+    against the live reference (other d, heap widths, query_topk; L2 and IP)."""
+    nlist, ts, ses = 1024, 200, 100
+    norm = metric == O.IP
+    nc, sg = (2500, 0.45) if norm else (400, 0.32)
+    xb = synth.clustered(seed, nb, d, nc, sg, normalize=norm)
+    xq = synth.clustered(seed + 100, ts + ses, d, nc, sg, normalize=norm)
+    cent = synth.clustered(seed + 200, nlist, d, nc, sg, normalize=norm)
+    orc = O.OracleIndex(d, nlist, metric)
+    orc.set_centroids(cent)
+    orc.add(xb)
+    ix = ab.IndexIVFFlat(d, nlist, metric)
+    ix.set_centroids(cent, compute_interdis=True)
+    ix.add(xb)
+    ok = np.ones(len(xq), bool)
+    if norm:  # queries the reference can run (arccos domain, first list >= k)
+        sizes = ix.list_sizes()
+        dis, keys = orc.coarse(xq, 1)
+        ok = (sizes[keys[:, 0]] >= k) & (dis[:, 0] <= 1.0)
+    cal = np.flatnonzero(ok[:ts])
+    tst = np.flatnonzero(ok[ts:]) + ts
+    cal, tst = cal[: len(cal) // 10 * 10], tst[: len(tst) // 10 * 10]
+    ts, ses = len(cal), len(tst)
+    assert ts >= 50 and ses >= 30
+    q = xq[np.concatenate([cal, tst])]
+    gD, gI = orc.search_fixed(q, k, nlist)
+    orc.calibrate(q[:ts], gD[:ts])
+    es = ab.Error_sys(ix, len(q), k)
+    es.set_gt(gD, gI)
+    es.sys_train(ts, q)
+    got = ix.traces()
+    assert len(got) == len(orc.traces)
+    for a, b in zip(got, orc.traces):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    for mult, stdm, eb in [(1.0, 1.0, 0.1), (4.0, 3.0, 0.05), (7.9, 6.0, 0.2)]:
+        acc = np.full(ts + ses, 1 - eb, np.float32)
+        acc[::4] = 1 - eb / 3
+        orc.multipler, orc.std_m = mult, stdm
+        D2, I2, mynp, _ = orc.search_bounded(q[ts:], k, qk, acc, gt_D=gD, offset=ts, profile=False)
+        ix.set_params(mult, stdm)
+        D, I, np_gpu = ix.search_bounded(q[ts:], k, qk, acc[ts:])
+        assert ix.stats()["err_bits"] == 0 and orc.last_err == 0
+        assert np.array_equal(np_gpu, mynp[ts:]), (mult, stdm, eb)
+        assert np.array_equal(D, D2)
+        assert_results_match(D, I, D2, I2, what=f"bounded d={d} {mult},{stdm},{eb}")
