@@ -21,6 +21,7 @@ SYMBOLS = {
     "auncel_index_nlist": (C.c_int64, [_h]),
     "auncel_index_ntotal": (C.c_int64, [_h]),
     "auncel_index_is_trained": (C.c_int, [_h]),
+    "auncel_index_wait_stream": (C.c_int, [_h, C.c_void_p]),
     "auncel_index_set_centroids": (C.c_int, [_h, _f, C.c_int]),
     "auncel_index_get_centroids": (C.c_int, [_h, _f]),
     "auncel_index_get_interdis": (C.c_int, [_h, _f]),

@@ -306,6 +306,16 @@ int64_t auncel_index_nlist(const AuncelIndex* idx) { return idx->ix.nlist; }
 int64_t auncel_index_ntotal(const AuncelIndex* idx) { return idx->ix.ntotal; }
 int auncel_index_is_trained(const AuncelIndex* idx) { return idx->ix.trained ? 1 : 0; }
 
+int auncel_index_wait_stream(AuncelIndex* idx, void* cuda_stream) {
+    API_TRY
+    LOCK(idx);
+    IvfIndex& ix = idx->ix;
+    CUDA_CHECK(cudaSetDevice(ix.device));
+    CUDA_CHECK(cudaEventRecord(ix.ev_in, (cudaStream_t)cuda_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(ix.stream, ix.ev_in, 0));
+    API_CATCH
+}
+
 int auncel_index_set_centroids(AuncelIndex* idx, const float* centroids, int compute_interdis) {
     API_TRY
     LOCK(const_cast<AuncelIndex*>(idx));
@@ -614,6 +624,9 @@ int auncel_index_get_stats(const AuncelIndex* idx, double* out8) {
     out8[20] = (double)st.tc_staged;
     out8[21] = (double)st.simt_uniq;
     out8[22] = (double)st.simt_staged;
+    out8[23] = (double)st.tc_audit_bad;
+    out8[24] = (double)st.tc_audit_slots;
+    out8[25] = (double)st.tc_audit_cands;
     out8[0] = (double)st.nq;
     out8[1] = (double)st.nlist;
     out8[2] = (double)st.ndis;
@@ -629,6 +642,7 @@ int auncel_index_set_option(AuncelIndex* idx, const char* name, int value) {
     API_TRY
     std::string n(name ? name : "");
     if (n == "tensor_core_filter") idx->ix.tc_mode = value;      // 0 off, 1 auto, 2 whenever heaps are full
+    else if (n == "tc_audit") idx->ix.tc_audit = value;          // tests: exact rescan + comparison of every tensor-core round
     else if (n == "exact_ties") idx->ix.exact_ties = value != 0;  // replay the reference's heap order
     else AUNCEL_THROW(-2, "unknown option " + n);
     API_CATCH

@@ -79,6 +79,8 @@ struct SearchStats {  // IndexIVFStats, IndexIVF.h:361-374
     double coarse_ms = 0;
     double scan_ms = 0;      // device time of the scan kernels of the last search
     uint64_t err_bits = 0;   // ERR_* bits raised by the last search
+    // option "tc_audit": slots of tensor-core rounds compared with an exact rescan of the round
+    uint64_t tc_audit_bad = 0, tc_audit_slots = 0, tc_audit_cands = 0;
 };
 
 // per-query arguments of a search call; all pointers are DEVICE pointers
@@ -151,6 +153,10 @@ struct IvfIndex {
     DevBuf<unsigned long long> tc_cand;      // survivors of the tensor-core filter
     DevBuf<int> pair_flag;                   // per slot: overflowed in a tensor-core round
     int tc_mode = 1;                         // 0 off, 1 automatic, 2 whenever every active heap is full
+    int tc_audit = 0;                        // tests: redo every tensor-core round exactly and compare the slots
+    DevBuf<unsigned char> audit_pool;
+    DevBuf<int> audit_cnt;
+    DevBuf<unsigned long long> audit_ctr;
     DevBuf<int> ctl;           // small control block (counters)
     PinnedBuf<int> h_ctl;
     DevBuf<float> io_f;        // host-API staging
@@ -161,6 +167,7 @@ struct IvfIndex {
     size_t pool_budget_bytes = (size_t)4 << 30;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    cudaEvent_t ev_in = nullptr;  // auncel_index_wait_stream: orders this stream behind a caller stream
     std::vector<cudaEvent_t> scan_ev;  // pairs of events around every scan launch
     std::vector<cudaEvent_t> tc_ev;    // pairs of events around every tensor-core filter launch
     DevBuf<unsigned long long> round_work;

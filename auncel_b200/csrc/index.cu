@@ -22,6 +22,7 @@ IvfIndex::IvfIndex(int d_, long nlist_, int metric_, int device_)
     CUDA_CHECK(cudaEventCreate(&ev0));
     CUDA_CHECK(cudaEventCreate(&ev1));
     CUDA_CHECK(cudaEventCreate(&ev2));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
     h_list_off.assign(nlist + 1, 0);
     list_off.ensure(nlist + 1);
     CUDA_CHECK(cudaMemset(list_off.p, 0, (nlist + 1) * sizeof(long long)));
@@ -42,6 +43,7 @@ IvfIndex::~IvfIndex() {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (ev2) cudaEventDestroy(ev2);
+    if (ev_in) cudaEventDestroy(ev_in);
     for (auto e : scan_ev) cudaEventDestroy(e);
     for (auto e : tc_ev) cudaEventDestroy(e);
 }
@@ -365,6 +367,7 @@ void IvfIndex::search(const QueryBatch& qb) {
         AUNCEL_CHECK(qb.require_acc != nullptr, "require_acc missing");
     }
     stats = SearchStats();
+    if (tc_audit) CUDA_CHECK(cudaMemsetAsync(audit_ctr.ensure(8), 0, 8 * sizeof(unsigned long long), stream));
     round_log.clear();
     debug_rounds = getenv("AUNCEL_DEBUG_ROUNDS") != nullptr;
     CUDA_CHECK(cudaEventRecord(ev0, stream));
@@ -600,6 +603,23 @@ void IvfIndex::search(const QueryBatch& qb) {
             } else {
                 stats.tc_rounds++;
                 scanned = true;
+                if (tc_audit) {
+                    // exact rescan of the whole round into a second pool, slot-by-slot comparison
+                    RoundParams ra = rp;
+                    ra.qt = SCAN_QT;
+                    ra.unsorted = 0;
+                    ra.defer_sort = 0;
+                    ra.pair_flag = nullptr;
+                    const size_t aslots = (size_t)n_active * w;
+                    audit_pool.ensure(aslots * K * 8);
+                    ra.cand_d = reinterpret_cast<float*>(audit_pool.p);
+                    ra.cand_off = reinterpret_cast<unsigned*>(audit_pool.p + aslots * K * 4);
+                    ra.slot_cnt = audit_cnt.ensure(aslots);
+                    ra.round_work = audit_ctr.ensure(8) + 4;
+                    launch_plan(ra, stream);
+                    launch_scan(ra, codes_tmap, qmap, num_sms, stream);
+                    launch_tc_audit(rp, ra.cand_d, ra.cand_off, ra.slot_cnt, audit_ctr.p, stream);
+                }
                 if (h_ctl.p[CTL_OVERFLOW] > 0) {
                     // some (query, list) pairs had more than K survivors (loose or missing tau):
                     // the exact scan redoes just those pairs and rewrites their slots
@@ -681,6 +701,13 @@ void IvfIndex::search(const QueryBatch& qb) {
     CUDA_CHECK(cudaEventElapsedTime(&cms, ev0, ev2));
     stats.coarse_ms = cms;
     stats.err_bits = (uint64_t)h_ctl.p[CTL_ERR];
+    if (tc_audit) {
+        unsigned long long h_a[3];
+        CUDA_CHECK(cudaMemcpy(h_a, audit_ctr.p, sizeof(h_a), cudaMemcpyDeviceToHost));
+        stats.tc_audit_bad = h_a[0];
+        stats.tc_audit_slots = h_a[1];
+        stats.tc_audit_cands = h_a[2];
+    }
 }
 
 }  // namespace auncel

@@ -356,12 +356,14 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                             pass = __fmaf_rn(c.x, snv, dot) > c.y;
                         hits |= (pass ? 1u : 0u) << j;
                     }
-                    if (!valid) hits = 0;
+                    // once the survivor list is full the round is redone anyway: stop counting, so the
+                    // (signed) counter can never wrap however many pairs pass a loose threshold
+                    if (!valid || *reinterpret_cast<volatile int*>(&rp.ctl[CTL_OVERFLOW]) < 0) hits = 0;
                     while (hits) {
                         const int j = __ffs(hits) - 1;
                         hits &= hits - 1;
                         const int pos = atomicAdd(&rp.ctl[CTL_NCAND], 1);
-                        if (pos < ta.cand_cap)
+                        if ((unsigned)pos < (unsigned)ta.cand_cap)
                             ta.cand[pos] = ((unsigned long long)(unsigned)(pair0 + cg * 32 + j) << 32) | (unsigned)v;
                         else
                             rp.ctl[CTL_OVERFLOW] = -(1 << 30);  // survivor list full: the whole round is redone
@@ -391,7 +393,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
 // Survivors of the filter, recomputed with the reference's arithmetic and test.
 template <int METRIC>
 __global__ void rerank_kernel(RoundParams rp, TcArgs ta) {
-    const int ncand = min(rp.ctl[CTL_NCAND], ta.cand_cap);
+    const int ncand = (int)min((unsigned)rp.ctl[CTL_NCAND], (unsigned)ta.cand_cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += gridDim.x * blockDim.x) {
         const unsigned long long c = ta.cand[i];
         const int pos = (int)(c >> 32);
@@ -418,6 +420,44 @@ __global__ void rerank_kernel(RoundParams rp, TcArgs ta) {
             }
         }
     }
+}
+
+// Audit (option "tc_audit", tests only): the exact scan has redone the whole round into a second
+// pool; every slot the filter path did not flag as overflowed must hold exactly the same set of
+// (distance, offset) candidates -- i.e. no pair the reference's strict test accepts was dropped.
+__global__ void tc_audit_kernel(RoundParams tc, const float* __restrict__ ex_d, const unsigned* __restrict__ ex_off,
+                                const int* __restrict__ ex_cnt, unsigned long long* __restrict__ ctr) {
+    const long slot = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (slot >= (long)tc.n_active * tc.w) return;
+    if (tc.pair_flag[slot]) return;  // more than K survivors: the exact scan rewrites this slot anyway
+    const int K = tc.K;
+    const int c1 = tc.slot_cnt[slot] & ~SLOT_SORTED, c2 = ex_cnt[slot] & ~SLOT_SORTED;
+    bool bad = c1 != c2;
+    if (!bad)
+        for (int i = lane; i < c2; i += 32) {
+            const float dv = ex_d[slot * K + i];
+            const unsigned ov = ex_off[slot * K + i];
+            bool found = false;
+            for (int j = 0; j < c1; j++)
+                found |= (tc.cand_off[slot * K + j] == ov) &&
+                         (__float_as_uint(tc.cand_d[slot * K + j]) == __float_as_uint(dv));
+            bad |= !found;
+        }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        if (bad) atomicAdd(ctr, 1ull);
+        atomicAdd(ctr + 1, 1ull);
+        atomicAdd(ctr + 2, (unsigned long long)c2);
+    }
+}
+
+void launch_tc_audit(const RoundParams& tc, const float* ex_d, const unsigned* ex_off, const int* ex_cnt,
+                     unsigned long long* ctr, cudaStream_t s) {
+    const long slots = (long)tc.n_active * tc.w;
+    if (slots == 0) return;
+    tc_audit_kernel<<<(unsigned)((slots * 32 + 255) / 256), 256, 0, s>>>(tc, ex_d, ex_off, ex_cnt, ctr);
+    CUDA_CHECK(cudaGetLastError());
 }
 
 // ||v||^2 of every arena row (double accumulation, rounded to float)

@@ -17,6 +17,8 @@ void launch_row_norms(const float* x, long long n, int dpad, float* out, cudaStr
 void launch_tc_filter(const RoundParams& rp, const TcArgs& ta, const void* codes_map, const void* queries_map,
                       int num_sms, cudaStream_t s);
 void launch_rerank(const RoundParams& rp, const TcArgs& ta, int num_sms, cudaStream_t s);
+void launch_tc_audit(const RoundParams& tc, const float* ex_d, const unsigned* ex_off, const int* ex_cnt,
+                     unsigned long long* ctr, cudaStream_t s);
 // tensor map over xq_sorted with an N-row, 128B-swizzled box (the MMA's B operand)
 void make_queries_tensor_map_tc(void* out_map, const float* xq_sorted, long long nrows, int dpad, int N);
 

@@ -102,10 +102,18 @@ class IndexIVFFlat:
         pre = None if precomputed_idx is None else _i64(precomputed_idx)
         _ck(lib().auncel_index_add(self.h, len(x), _p(x, _f), _p(xids, _l), _p(pre, _l)))
 
+    def _after(self, t):
+        """Stream contract of the `_device` entry points (include/auncel_b200.h): the index runs on
+        its own stream, so it is ordered behind whatever torch still has pending on the current
+        stream of the tensor's device (the copy or kernel that produces the inputs)."""
+        import torch
+        _ck(lib().auncel_index_wait_stream(self.h, torch.cuda.current_stream(t.device).cuda_stream))
+
     def add_device(self, x_t, xids=None, precomputed_idx=None):
         assert x_t.is_cuda and x_t.is_contiguous() and x_t.dtype.is_floating_point and x_t.element_size() == 4
         xids = None if xids is None else _i64(xids)
         pre = None if precomputed_idx is None else _i64(precomputed_idx)
+        self._after(x_t)
         _ck(lib().auncel_index_add_device(self.h, x_t.shape[0], x_t.data_ptr(), _p(xids, _l), _p(pre, _l)))
 
     def assign(self, x):
@@ -139,6 +147,7 @@ class IndexIVFFlat:
         return D, I
 
     def search_device(self, x_t, k, D_t, I_t):
+        self._after(x_t)
         _ck(lib().auncel_index_search_device(self.h, x_t.shape[0], x_t.data_ptr(), k, self.nprobe, self.max_codes,
                                              D_t.data_ptr(), I_t.data_ptr()))
 
@@ -189,18 +198,20 @@ class IndexIVFFlat:
 
     def search_bounded_device(self, x_t, max_topk, query_topk, acc_t, np_t, D_t, I_t, gt_t=None, trec_t=None,
                               flags=0):
+        self._after(x_t)
         _ck(lib().auncel_index_search_bounded_device(
             self.h, x_t.shape[0], x_t.data_ptr(), max_topk, query_topk, acc_t.data_ptr(),
             None if gt_t is None else gt_t.data_ptr(), np_t.data_ptr(),
             None if trec_t is None else trec_t.data_ptr(), flags, D_t.data_ptr(), I_t.data_ptr()))
 
     def stats(self):
-        out = (C.c_double * 24)()
+        out = (C.c_double * 32)()
         lib().auncel_index_get_stats(self.h, out)
         return dict(zip(["nq", "nlist", "ndis", "search_ms", "rounds", "scan_tiles", "scan_pairs", "err_bits",
                          "scan_ms", "launches", "scan_launches", "coarse_ms", "tc_rounds", "tc_candidates",
                          "tc_fallbacks", "tc_ms", "tc_ndis", "simt_ms", "simt_ndis", "tc_uniq", "tc_staged",
-                         "simt_uniq", "simt_staged"], [float(v) for v in out]))
+                         "simt_uniq", "simt_staged", "tc_audit_bad", "tc_audit_slots", "tc_audit_cands"],
+                        [float(v) for v in out]))
 
     def set_option(self, name, value):
         _ck(lib().auncel_index_set_option(self.h, name.encode(), int(value)))

@@ -12,7 +12,11 @@
  * Each entry point names the reference interface it replaces (paths relative to
  * /root/reference/Auncel).  "host" entry points take host pointers and do their own
  * host<->device copies; "_device" entry points take device pointers on the index's device
- * and enqueue on the index's stream, returning after the results are complete.
+ * and enqueue on the index's own (non-blocking) stream, returning after the results are
+ * complete.  STREAM CONTRACT: the index stream is not ordered against any other stream.  If
+ * the inputs of a "_device" call are produced by work still pending on another stream (a
+ * cudaMemcpyAsync, a kernel of the caller), call auncel_index_wait_stream(idx, that_stream)
+ * first (or synchronise that stream); outputs are complete when the call returns.
  */
 #ifndef AUNCEL_B200_H
 #define AUNCEL_B200_H
@@ -46,6 +50,10 @@ int auncel_index_d(const AuncelIndex* idx);
 int64_t auncel_index_nlist(const AuncelIndex* idx);
 int64_t auncel_index_ntotal(const AuncelIndex* idx);   /* Index::ntotal */
 int auncel_index_is_trained(const AuncelIndex* idx);   /* Index::is_trained */
+
+/* Orders the index's stream behind everything enqueued so far on `cuda_stream` (a cudaStream_t;
+ * NULL = the legacy default stream): event record + cudaStreamWaitEvent, no host wait. */
+int auncel_index_wait_stream(AuncelIndex* idx, void* cuda_stream);
 
 /* Import trained centroids (nlist x d, host) into the coarse quantizer -- the state
  * Level1Quantizer::train_q1 leaves behind (IndexIVF.cpp:71-137).  compute_interdis != 0 also
@@ -139,12 +147,15 @@ int auncel_index_search_bounded_device(AuncelIndex* idx, int64_t n, const float*
  * [15]=tensor-core filter kernel ms [16]=distance evaluations those launches covered
  * [17]=scan-phase ms of exact-scan rounds [18]=distance evaluations of those rounds
  * [19]/[21]=vectors of the distinct lists touched per launch, summed (tensor-core / exact rounds)
- * [20]/[22]=vectors staged into shared memory (one list pass per query tile).  out: 24 doubles */
-int auncel_index_get_stats(const AuncelIndex* idx, double* out24);
+ * [20]/[22]=vectors staged into shared memory (one list pass per query tile)
+ * [23..25] option "tc_audit": slots that differ from the exact rescan / slots compared / candidates compared.
+ * out: 32 doubles */
+int auncel_index_get_stats(const AuncelIndex* idx, double* out32);
 
 /* engine switches (results never change): "tensor_core_filter" 0 off / 1 automatic / 2 whenever
  * every active query holds K results; "exact_ties" 0/1 replay of the reference's heap order for
- * equal centroid distances */
+ * equal centroid distances; "tc_audit" 0/1 (tests) redo every tensor-core round with the exact scan and
+ * compare the candidate slots */
 int auncel_index_set_option(AuncelIndex* idx, const char* name, int value);
 
 /* scratch budget for per-round candidate pools, bytes (default 4 GiB) */

@@ -81,6 +81,14 @@ def test_bounded_search_properties(big):
     assert np.all(np.diff(D, axis=1) >= 0) and np.all(D >= gD[600:])
     rec = W.recall_at(gD[600:], D, 10, 1)
     assert (rec >= 0.9 - 1e-6).mean() > 0.95  # the authors' hyper-parameters hold the bound on this data
+    # every tensor-core round audited against an exact rescan (option "tc_audit"): nothing dropped
+    ix.set_option("tc_audit", 1)
+    es.set_queries(600, q.cpu().numpy(), acc, 1200)
+    Da, Ia = es.search(600)
+    sa = ix.stats()
+    ix.set_option("tc_audit", 0)
+    assert sa["tc_audit_slots"] > 0 and sa["tc_audit_bad"] == 0, sa
+    assert np.array_equal(Da, D) and np.array_equal(Ia, I)
     # ndis == sum of the sizes of the lists each query scanned (IndexIVF.cpp:676)
     sizes = ix.list_sizes()
     _, keys = ix.coarse_search(q[600:].cpu().numpy(), NLIST)

@@ -171,6 +171,30 @@ def test_merge_tables_and_shards():
     assert np.array_equal(D, D2) and np.array_equal(I, I2)
 
 
+@pytest.mark.parametrize("metric", [O.L2, O.IP])
+@pytest.mark.parametrize("nshard,k", [(2, 10), (5, 33), (8, 100), (17, 7), (64, 128)])
+def test_merge_tables_tie_order(metric, nshard, k):
+    """Equal distances arriving from different shards leave the merge in the order of the
+    reference's size-nshard heap (IndexShards.cpp:86-101 with Heap.h push/pop), not merely sorted:
+    labels must be identical, ties included."""
+    rng = np.random.default_rng(nshard * 1000 + k)
+    n = 257
+    vals = rng.integers(0, 12, size=(nshard, n, k)).astype(np.float32)  # few distinct values: ties everywhere
+    vals.sort(axis=2)
+    if metric == O.IP:
+        vals = vals[:, :, ::-1].copy()
+    labels = rng.integers(0, 1 << 40, size=(nshard, n, k)).astype(np.int64)
+    cut = rng.integers(0, k + 1, size=(nshard, n))
+    for s in range(nshard):
+        for q in range(0, n, 3):
+            labels[s, q, cut[s, q]:] = -1  # rows that end early; some shards contribute nothing
+    tr = rng.integers(0, 1000, size=nshard).astype(np.int64)
+    D, I = ab.merge_tables(metric, vals, labels, tr)
+    D2, I2 = O.merge_tables(metric, vals, labels, tr)
+    assert np.array_equal(D, D2)
+    assert np.array_equal(I, I2)
+
+
 def test_train_kmeans_runs_and_searches():
     d, nlist = 16, 64
     xb = synth.clustered(41, 20000, d, 30)

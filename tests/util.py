@@ -65,3 +65,22 @@ def recall_at(gt_D, D, qk, metric):
     else:
         hit = D[:, :qk] >= t - 1e-6
     return hit.sum(1) / float(qk)
+
+
+def mixture(seed, n, d, normalize=False, n_centers=1024, lowrank=16, sigma_lr=1.2, sigma_iso=0.5):
+    """Host copy of auncel_b200.workload.make_vectors' mixture (centre + rank-16 + isotropic
+    noise) on numpy's PCG64, for CPU-vs-GPU parity tests at the BASELINE.json shapes."""
+    gp = np.random.default_rng(977)
+    centers = gp.standard_normal((n_centers, d), dtype=np.float32)
+    basis = gp.standard_normal((lowrank, d), dtype=np.float32) / np.float32(np.sqrt(lowrank))
+    g = np.random.default_rng(seed)
+    out = np.empty((n, d), np.float32)
+    for i0 in range(0, n, 1 << 16):
+        m = min(1 << 16, n - i0)
+        x = centers[g.integers(0, n_centers, m)]
+        x = x + np.float32(sigma_lr) * (g.standard_normal((m, lowrank), dtype=np.float32) @ basis)
+        x = x + np.float32(sigma_iso) * g.standard_normal((m, d), dtype=np.float32)
+        if normalize:
+            x = x / np.sqrt((x * x).sum(1, keepdims=True))
+        out[i0:i0 + m] = x
+    return out
