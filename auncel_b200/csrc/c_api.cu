@@ -4,7 +4,6 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
-#include <random>
 #include <utility>
 
 #include "../../include/auncel_b200.h"
@@ -52,128 +51,6 @@ void h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
 }
 void d2h(void* dst, const void* src, size_t bytes, cudaStream_t s) {
     if (bytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
-}
-
-// ---- Clustering::train (Clustering.cpp:77-244) with the assignment step on the device ----
-void rand_perm(std::vector<int>& perm, size_t n, long seed) {  // utils.cpp:229-239
-    perm.resize(n);
-    for (size_t i = 0; i < n; i++) perm[i] = (int)i;
-    std::mt19937 mt((unsigned int)seed);
-    for (size_t i = 0; i + 1 < n; i++) {
-        int i2 = (int)(i + mt() % (n - i));
-        std::swap(perm[i], perm[i2]);
-    }
-}
-
-float sse_norm2(const float* x, int d) {  // fvec_norm_L2sqr, utils_simd.cpp:137-155
-    float s[4] = {0, 0, 0, 0};
-    int j = 0;
-    for (; j + 4 <= d; j += 4)
-        for (int l = 0; l < 4; l++) s[l] = fadd(s[l], fmul(x[j + l], x[j + l]));
-    for (int l = 0; l < 4; l++) {
-        float v = j + l < d ? x[j + l] : 0.f;
-        s[l] = fadd(s[l], fmul(v, v));
-    }
-    return fadd(fadd(s[0], s[1]), fadd(s[2], s[3]));
-}
-
-void renorm(std::vector<float>& c, long k, int d) {  // fvec_renorm_L2, utils.cpp:377-392
-    for (long i = 0; i < k; i++) {
-        float* xi = c.data() + i * d;
-        float nr = sse_norm2(xi, d);
-        if (nr > 0) {
-            const float inv_nr = 1.0 / sqrtf(nr);
-            for (int j = 0; j < d; j++) xi[j] *= inv_nr;
-        }
-    }
-}
-
-int km_update_centroids(const float* x, float* centroids, const long long* assign, size_t d, size_t k,
-                        size_t n) {  // utils.cpp:1078-1161
-    std::vector<size_t> hassign(k, 0);
-    memset(centroids, 0, sizeof(float) * d * k);
-    for (size_t i = 0; i < n; i++) {
-        size_t ci = (size_t)assign[i];
-        float* c = centroids + ci * d;
-        const float* xi = x + i * d;
-        hassign[ci]++;
-        for (size_t j = 0; j < d; j++) c[j] += xi[j];
-    }
-    for (size_t ci = 0; ci < k; ci++) {
-        float* c = centroids + ci * d;
-        float ni = (float)hassign[ci];
-        if (ni != 0)
-            for (size_t j = 0; j < d; j++) c[j] /= ni;
-    }
-    const double EPS = 1 / 1024.;
-    size_t nsplit = 0;
-    std::mt19937 mt(1234);
-    for (size_t ci = 0; ci < k; ci++) {
-        if (hassign[ci] == 0) {
-            size_t cj;
-            for (cj = 0; 1; cj = (cj + 1) % k) {
-                float p = (hassign[cj] - 1.0) / (float)(n - k);
-                float r = mt() / float(mt.max());
-                if (r < p) break;
-            }
-            memcpy(centroids + ci * d, centroids + cj * d, sizeof(float) * d);
-            for (size_t j = 0; j < d; j++) {
-                if (j % 2 == 0) {
-                    centroids[ci * d + j] *= 1 + EPS;
-                    centroids[cj * d + j] *= 1 - EPS;
-                } else {
-                    centroids[ci * d + j] *= 1 - EPS;
-                    centroids[cj * d + j] *= 1 + EPS;
-                }
-            }
-            hassign[ci] = hassign[cj] / 2;
-            hassign[cj] -= hassign[ci];
-            nsplit++;
-        }
-    }
-    return (int)nsplit;
-}
-
-void train_kmeans(AuncelIndex_H* h, long nx, const float* x_in, int niter, bool tune) {
-    IvfIndex& ix = h->ix;
-    const long k = ix.nlist;
-    const int d = ix.d;
-    AUNCEL_CHECK(nx >= k, "Number of training points should be at least as large as number of clusters");
-    for (size_t i = 0; i < (size_t)nx * d; i++)
-        AUNCEL_CHECK(std::isfinite(x_in[i]), "input contains NaN's or Inf's");
-    const long max_pts = 256, seed = 1234;
-    std::vector<float> sub;
-    const float* x = x_in;
-    if (nx > k * max_pts) {
-        std::vector<int> perm;
-        rand_perm(perm, nx, seed);
-        nx = k * max_pts;
-        sub.resize((size_t)nx * d);
-        for (long i = 0; i < nx; i++) memcpy(sub.data() + (size_t)i * d, x_in + (size_t)perm[i] * d, sizeof(float) * d);
-        x = sub.data();
-    }
-    std::vector<float> cent((size_t)k * d);
-    if (nx == k) {
-        memcpy(cent.data(), x_in, sizeof(float) * d * k);
-        ix.set_centroids(cent.data(), tune);
-        return;
-    }
-    std::vector<int> perm;
-    rand_perm(perm, nx, seed + 1);
-    for (long i = 0; i < k; i++) memcpy(&cent[(size_t)i * d], x + (size_t)perm[i] * d, d * sizeof(float));
-    const bool spherical = ix.metric == METRIC_IP;  // IndexIVF.cpp:160-162
-    if (spherical) renorm(cent, k, d);
-    CUDA_CHECK(cudaSetDevice(ix.device));
-    h->x.ensure((size_t)nx * d);
-    h2d(h->x.p, x, (size_t)nx * d * sizeof(float), ix.stream);
-    std::vector<long long> assign(nx);
-    for (int it = 0; it < niter; it++) {
-        ix.set_centroids(cent.data(), false);
-        ix.assign_device(nx, h->x.p, assign.data());
-        km_update_centroids(x, cent.data(), assign.data(), d, k, nx);
-        if (spherical) renorm(cent, k, d);
-    }
-    ix.set_centroids(cent.data(), tune);
 }
 
 // ---- Trace::SB (IVF_pro.cpp:109-149): same std::sort call, same running means ----
@@ -345,7 +222,7 @@ int auncel_index_set_interdis(AuncelIndex* idx, const float* in) {
 int auncel_index_train(AuncelIndex* idx, int64_t n, const float* x, int niter, int tune) {
     API_TRY
     LOCK(const_cast<AuncelIndex*>(idx));
-    train_kmeans(idx, (long)n, x, niter > 0 ? niter : 25, tune != 0);  // cp.niter = 25, IndexIVF.cpp:54
+    train_kmeans(idx->ix, (long)n, x, niter > 0 ? niter : 25, tune != 0);  // cp.niter = 25, IndexIVF.cpp:54
     API_CATCH
 }
 

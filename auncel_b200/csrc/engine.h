@@ -92,7 +92,8 @@ struct QueryBatch {
     long max_codes = 0;
     int mode = 0;              // 0 fixed, 1 tune (error bounded), 2 training (calibration)
     int query_topk = 0;
-    const float* require_acc = nullptr;  // n
+    const float* require_acc = nullptr;  // n (time_tune: the latency budget in ms, IndexIVF.cpp:547)
+    int time_tune = 0;                   // error_pro::time_tune: latency-budget cut after every list (:545-549)
     const float* gt_kth = nullptr;       // n, GT distance at rank query_topk-1 (profile)
     unsigned long long* my_nprobe = nullptr;  // n, in/out
     float* t_recalls = nullptr;          // n, in/out
@@ -164,6 +165,15 @@ struct IvfIndex {
     DevBuf<unsigned long long> io_u;
     DevBuf<unsigned long long> assign_best;
 
+    // range search (range.cu): results of the last call stay here until they are fetched
+    DevBuf<unsigned long long> range_off, range_lims;
+    DevBuf<float> range_D;
+    DevBuf<long long> range_I;
+    long long range_total = 0;
+    // clock model of the latency-budget mode (IndexIVF::time(), IndexIVF.cpp:329-333): cost of one
+    // probe iteration / of one scanned code.  Default: a B200 streaming a list at HBM speed.
+    long long time_us_per_list = 2, time_ns_per_code = 0;
+
     size_t pool_budget_bytes = (size_t)4 << 30;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -198,6 +208,8 @@ struct IvfIndex {
     // coarse: ranks all nlist centroids for n staged queries (x_dev n x d) into c_dis/c_keys
     void coarse_rank(long n, const float* x_dev);
     void search(const QueryBatch& qb);
+    // IndexIVF::range_search: lims_host gets n + 1 offsets; distances / labels stay in range_D / range_I
+    void range_search(long n, const float* x_dev, float radius, int nprobe, long long* lims_host);
     int max_num() const { return (int)(nlist / 8 + 20); }
     int expected_traces() const { int t = 0; for (long p = 1; p <= nlist / 8; p <<= 1) t++; return t; }
     ErrModelView model_view() const;
@@ -219,5 +231,8 @@ void launch_interdis(int metric, const float* cent, long nlist, int dpad, float*
 void launch_merge_tables(int metric, long n, long k, long nshard, const float* all_D,
                          const long long* all_I, const long long* translations, float* D,
                          long long* I, cudaStream_t s);
+
+// Index::train: k-means on the device (kmeans.cu), then set_centroids
+void train_kmeans(IvfIndex& ix, long nx, const float* x_host, int niter, bool tune);
 
 }  // namespace auncel

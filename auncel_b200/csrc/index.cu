@@ -421,6 +421,10 @@ void IvfIndex::search(const QueryBatch& qb) {
     tp.overhead_profile = qb.overhead_profile;
     tp.nprobe = nprobe;
     tp.max_codes = qb.max_codes;
+    tp.time_tune = qb.time_tune;
+    tp.us_per_list = time_us_per_list;
+    tp.ns_per_code = time_ns_per_code;
+    if (qb.time_tune) AUNCEL_CHECK(qb.require_acc != nullptr, "time_tune needs the per-query budget (require_acc, ms)");
     tp.model = model_view();
     tp.require_acc = qb.require_acc;
     tp.gt_kth = qb.gt_kth;

@@ -21,15 +21,32 @@ __global__ void init_state_kernel(RoundParams rp, TuneParams tp, const unsigned 
     long q = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (q >= rp.n) return;
     int limit = tp.nprobe, cut = 0;
-    if (tp.max_codes > 0) {  // IndexIVF.cpp:541-543
+    if (tp.max_codes > 0 || tp.time_tune) {
+        // Both cuts depend only on the sizes of the lists along the probe order, so the stage at which
+        // the reference breaks is known before anything is scanned.
         long cum = 0;
+        unsigned long long vt_ns = 0;
+        const double t0 = 0.0;  // IndexIVF::time() at the start of the query, on the modelled clock
+        const double budget = tp.time_tune ? dmul((double)tp.require_acc[q], 0.95) : 0.0;
         for (int p = 0; p < tp.nprobe; p++) {
             int l = rp.ckeys[q * rp.nlist + p];
-            cum += rp.list_off[l + 1] - rp.list_off[l];
-            if (cum >= tp.max_codes) {
+            const long long sz = rp.list_off[l + 1] - rp.list_off[l];
+            cum += sz;
+            if (tp.max_codes > 0 && cum >= tp.max_codes) {  // IndexIVF.cpp:541-543
                 limit = p + 1;
                 cut = 1;
                 break;
+            }
+            if (tp.time_tune) {  // IndexIVF.cpp:545-549; time() = tv_sec + tv_usec * 1e-6 (:329-333)
+                vt_ns += (unsigned long long)tp.us_per_list * 1000ull + (unsigned long long)sz * (unsigned long long)tp.ns_per_code;
+                const unsigned long long us = vt_ns / 1000ull;
+                const double now = dadd((double)(us / 1000000ull), dmul((double)(us % 1000000ull), 1e-6));
+                const double el = dmul(dsub(now, t0), 1000.0);
+                if (el >= dsub(budget, __ddiv_rn(el, (double)(p + 1)))) {
+                    limit = p + 1;
+                    cut = 1;
+                    break;
+                }
             }
         }
     }

@@ -9,6 +9,8 @@ struct TuneParams {
     int profile, overhead_profile;
     int nprobe;
     long max_codes;
+    int time_tune;                     // latency-budget cut (IndexIVF.cpp:545-549) on the modelled clock
+    long long us_per_list, ns_per_code;
     ErrModelView model;
     const float* require_acc;          // n (device)
     const float* gt_kth;               // n or null

@@ -434,6 +434,24 @@ static size_t scan_codes(int metric, int d, const float* xi, size_t list_size, c
  *   (pre_num, recall_after_plateau, ext, my_nprobe_after_stage); untouched stages keep -2.
  * Returns an error bitmask (0 = clean): see arcos_lookup / orc_cosine_theorem.
  */
+/* error_pro::time_tune (IVF_pro.h:82-114): the latency-budget cut of Error_sys::time_search
+ * (profile.cpp:229-244, IndexIVF.cpp:545-549).  The reference reads the wall clock
+ * (IndexIVF::time(), :329-333: gettimeofday -> tv_sec + tv_usec * 1e-6); here the clock is a
+ * model: every probe iteration that reaches the check costs us_per_list microseconds plus
+ * ns_per_code nanoseconds per scanned code, and time() is evaluated on the resulting
+ * (tv_sec, tv_usec) pair with the reference's arithmetic.  require_acc[id] is the budget in ms. */
+static int g_time_tune = 0;
+static long g_us_per_list = 0, g_ns_per_code = 0;
+void orc_set_time_tune(int on, long us_per_list, long ns_per_code) {
+    g_time_tune = on;
+    g_us_per_list = us_per_list;
+    g_ns_per_code = ns_per_code;
+}
+static double orc_vclock(unsigned long long total_ns) {
+    unsigned long long us = total_ns / 1000ull;
+    return (double)(us / 1000000ull) + (double)(us % 1000000ull) * 1e-6;
+}
+
 int orc_search_preassigned(int metric, int d, long nlist, const float* codes, const long* list_off,
                            const idx_t* ids, long n, const float* x, long k, long nprobe,
                            long max_codes, const idx_t* keys, const float* coarse_dis, int mode,
@@ -461,6 +479,8 @@ int orc_search_preassigned(int metric, int d, long nlist, const float* codes, co
         idx_t* idxi = I + i * k;
         heap_heapify(mx, k, simi, idxi); /* init_result, :421-427 */
         long nscan = 0;
+        unsigned long long vt_ns = 0;
+        double t0 = orc_vclock(0); /* :504-506 */
         size_t pre_num = 0, query_k = 0, stoped = 0;
         float true_KD_K = 0, pre_val = 0;
         if (tune) {
@@ -474,8 +494,10 @@ int orc_search_preassigned(int metric, int d, long nlist, const float* codes, co
         for (long ik = 0; ik < nprobe; ik++) { /* :526 */
             /* scan_one_list, :439-475 */
             idx_t key = keys[i * nprobe + ik];
+            vt_ns += (unsigned long long)g_us_per_list * 1000ull;
             if (key >= 0) {
                 size_t ls = list_off[key + 1] - list_off[key];
+                vt_ns += (unsigned long long)ls * (unsigned long long)g_ns_per_code;
                 if (ls != 0) {
                     nlistv++;
                     nheap += scan_codes(metric, d, xi, ls, codes + (size_t)list_off[key] * d,
@@ -484,6 +506,10 @@ int orc_search_preassigned(int metric, int d, long nlist, const float* codes, co
                 }
             }
             if (max_codes && nscan >= max_codes) break; /* :541-543 */
+            if (g_time_tune) { /* :545-549 */
+                double now = orc_vclock(vt_ns);
+                if ((now - t0) * 1000 >= require_acc[id_q] * 0.95 - (now - t0) * 1000 / (ik + 1)) break;
+            }
 
             if (tune) { /* :551-638 */
                 size_t stage = ik + 1;
@@ -591,6 +617,45 @@ int orc_search_preassigned(int metric, int d, long nlist, const float* codes, co
     free(c2c);
     free(tmp_simi);
     return err;
+}
+
+/* ------------------------------------------------------------------ range search */
+
+/* IndexIVF::range_search_preassigned (IndexIVF.cpp:760-860, parallel_mode 0) with
+ * IVFFlatScanner::scan_codes_range (IndexIVFFlat.cpp:139-155): every vector of the probed lists
+ * with C::cmp(radius, dis) -- L2: dis < radius, IP: dis > radius -- in scan order (probe rank, then
+ * in-list order).  Two passes like RangeSearchResult (AuxIndexStructures.h:31-50): out_D == NULL
+ * only fills lims[n + 1]; stats[0] += lists visited, stats[1] += codes scanned. */
+void orc_range_search(int metric, int d, const float* codes, const long* list_off, const idx_t* ids,
+                      long n, const float* x, float radius, long nprobe, const idx_t* keys, long* lims,
+                      float* out_D, idx_t* out_I, long* stats) {
+    int mx = metric == ORC_L2;
+    long pos = 0;
+    for (long i = 0; i < n; i++) {
+        lims[i] = pos;
+        for (long ik = 0; ik < nprobe; ik++) {
+            idx_t key = keys[i * nprobe + ik];
+            if (key < 0) continue;
+            long ls = list_off[key + 1] - list_off[key];
+            if (ls == 0) continue;
+            if (stats && !out_D) {
+                stats[0]++;
+                stats[1] += ls;
+            }
+            for (long j = 0; j < ls; j++) {
+                const float* yj = codes + (size_t)(list_off[key] + j) * d;
+                float dis = mx ? orc_fvec_L2sqr(x + i * d, yj, d) : orc_fvec_inner_product(x + i * d, yj, d);
+                if (mx ? (radius > dis) : (radius < dis)) {
+                    if (out_D) {
+                        out_D[pos] = dis;
+                        out_I[pos] = ids[list_off[key] + j];
+                    }
+                    pos++;
+                }
+            }
+        }
+    }
+    lims[n] = pos;
 }
 
 /* ------------------------------------------------------------------ shards */

@@ -87,6 +87,9 @@ def orc():
             C.c_float, C.c_long, _f, _f, C.c_int, C.c_int, _ul, _f, _f, C.c_long, _f, _l, _l,
             C.c_long, _f]
         lib.orc_merge_tables.argtypes = [C.c_int, C.c_long, C.c_long, C.c_long, _f, _l, _f, _l, _l]
+        lib.orc_set_time_tune.argtypes = [C.c_int, C.c_long, C.c_long]
+        lib.orc_range_search.argtypes = [C.c_int, C.c_int, _f, _l, _l, C.c_long, _f, C.c_float, C.c_long, _l, _l,
+                                         _f, _l, _l]
         _orc = lib
     return _orc
 
@@ -159,6 +162,10 @@ def ref():
         lib.ref_cosine_theorem.argtypes = [C.c_float, C.c_float, C.c_float]
         lib.ref_kscaling.restype = C.c_float
         lib.ref_kscaling.argtypes = [C.c_float, C.c_long, _f, C.c_long]
+        lib.ref_set_virtual_clock.argtypes = [C.c_int]
+        lib.ref_es_time_search.argtypes = [C.c_void_p, _f, _l, C.c_long, C.c_long, C.c_int]
+        lib.ref_range_search.argtypes = [C.c_void_p, C.c_long, _f, C.c_float, C.c_long, _l]
+        lib.ref_range_results.argtypes = [C.c_long, _f, _l]
         lib.ref_shim_set_blas.argtypes = [C.c_char_p]
         blas = find_openblas()
         if blas:
@@ -318,6 +325,29 @@ class RefIndex:
                 m = min(search_size, num - q)
                 _ck(self.lib.ref_es_search(self.h, _p(D[q:], _f), _p(I[q:], _l), start + q, m))
         return D, I
+
+    def es_time_search(self, start, num, virtual_clock=True):
+        """Error_sys::time_search (profile.cpp:229-244); require_acc = budget in ms.  With the
+        virtual clock every IndexIVF::time() call advances by exactly 1 s (ref_driver.cpp)."""
+        k = self.max_topk
+        D = np.empty((num, k), np.float32)
+        I = np.empty((num, k), np.int64)
+        self.lib.ref_set_virtual_clock(int(virtual_clock))
+        try:
+            _ck(self.lib.ref_es_time_search(self.h, _p(D, _f), _p(I, _l), start, num, 1))
+        finally:
+            self.lib.ref_set_virtual_clock(0)
+        return D, I
+
+    def range_search(self, x, radius, nprobe):
+        """IndexIVF::range_search (IndexIVF.cpp:741-860) -> (lims, D, I)."""
+        x = f32(x)
+        lims = np.empty(len(x) + 1, np.int64)
+        _ck(self.lib.ref_range_search(self.h, len(x), _p(x, _f), radius, nprobe, _p(lims, _l)))
+        D = np.empty(int(lims[-1]), np.float32)
+        I = np.empty(int(lims[-1]), np.int64)
+        self.lib.ref_range_results(int(lims[-1]), _p(D, _f), _p(I, _l))
+        return lims, D, I
 
     def my_nprobe(self, start, n):
         out = np.empty(n, np.uint64)
@@ -487,6 +517,33 @@ class OracleIndex:
     def search_fixed(self, x, k, nprobe, max_codes=0):
         dis, keys = self.coarse(x, nprobe)
         return self.search_preassigned(x, k, keys, dis, 0, max_codes)
+
+    def search_timed(self, x, k, budget_ms, us_per_list, ns_per_code, offset=0):
+        """Error_sys::time_search (profile.cpp:229-244): nprobe = nlist, no tune block, the
+        latency cut of IndexIVF.cpp:545-549 on the modelled clock (orc_set_time_tune)."""
+        dis, keys = self.coarse(x, self.nlist)
+        self.lib.orc_set_time_tune(1, int(us_per_list), int(ns_per_code))
+        try:
+            return self.search_preassigned(x, k, keys, dis, 0, 0, offset=offset, require_acc=budget_ms)
+        finally:
+            self.lib.orc_set_time_tune(0, 0, 0)
+
+    def range_search(self, x, radius, nprobe):
+        """IndexIVF::range_search (IndexIVF.cpp:741-860) -> (lims, D, I), hits in scan order."""
+        x = f32(x)
+        dis, keys = self.coarse(x, nprobe)
+        keys = i64(keys)
+        codes, off, ids = self.csr()
+        lims = np.empty(len(x) + 1, np.int64)
+        stats = np.zeros(2, np.int64)
+        args = (self.metric, self.d, _p(codes, _f), _p(off, _l), _p(ids, _l), len(x), _p(x, _f), radius, nprobe,
+                _p(keys, _l), _p(lims, _l))
+        self.lib.orc_range_search(*args, None, None, _p(stats, _l))
+        D = np.empty(int(lims[-1]), np.float32)
+        I = np.empty(int(lims[-1]), np.int64)
+        self.lib.orc_range_search(*args, _p(D, _f), _p(I, _l), None)
+        self.last_stats = dict(nlist=int(stats[0]), ndis=int(stats[1]))
+        return lims, D, I
 
     def n_traces(self):
         n, np_ = 0, 1

@@ -15,6 +15,7 @@
  *   IndexShards / IndexReplicas       Auncel/IndexShards.h, IndexReplicas.h
  */
 #include <omp.h>
+#include <sys/time.h>
 #include <unistd.h>
 
 #include <cmath>
@@ -30,6 +31,7 @@
 #include "IndexIVFFlat.h"
 #include "IndexReplicas.h"
 #include "IndexShards.h"
+#include "AuxIndexStructures.h"
 #include "profile.h"
 #include "utils.h"
 
@@ -284,6 +286,61 @@ int ref_es_set_queries(void* h, long query_topk, long num, const float* xq, long
     r->index->t->profile = profile != 0;
     r->index->t->overhead_profile = overhead_profile != 0;
     REF_CATCH
+}
+
+/* Deterministic clock for the latency-budget mode.  IndexIVF::time() (Auncel/IndexIVF.cpp:329-333) is
+ * gettimeofday(); the library is linked with -Bsymbolic-functions so the reference's calls bind to
+ * this definition.  Virtual mode: every call advances the clock by exactly one second (tv_usec = 0),
+ * so (now - t0) is an exact small integer and the break rule of :545-549 becomes reproducible;
+ * otherwise the real clock is returned (clock_gettime). */
+static int g_virtual_clock = 0;
+static long g_virtual_now = 1000;
+int gettimeofday(struct timeval* tv, void* tz) noexcept {
+    (void)tz;
+    if (g_virtual_clock) {
+        tv->tv_sec = ++g_virtual_now;
+        tv->tv_usec = 0;
+        return 0;
+    }
+    struct timespec ts;
+    clock_gettime(CLOCK_REALTIME, &ts);
+    tv->tv_sec = ts.tv_sec;
+    tv->tv_usec = ts.tv_nsec / 1000;
+    return 0;
+}
+void ref_set_virtual_clock(int on) { g_virtual_clock = on; }
+
+/* Error_sys::time_search (profile.cpp:229-244): require_acc[id] is the budget in ms.  The
+ * reference leaves error_pro::time_tune set afterwards (:242); `reset_flag` clears it again so
+ * later searches of the harness are unaffected. */
+int ref_es_time_search(void* h, float* D, long* I, long start, long search_size, int reset_flag) {
+    Ref* r = (Ref*)h;
+    REF_TRY
+    r->es->time_search(D, (int64_t*)I, start, (size_t)search_size);
+    if (reset_flag) r->index->t->time_tune = false;
+    REF_CATCH
+}
+
+/* IndexIVF::range_search (IndexIVF.cpp:741-860).  Two calls like RangeSearchResult's own life
+ * cycle: the first runs the search and returns lims (nq + 1), the second copies the buffers. */
+static faiss::RangeSearchResult* g_range = nullptr;
+int ref_range_search(void* h, long n, const float* x, float radius, long nprobe, long* lims) {
+    Ref* r = (Ref*)h;
+    REF_TRY
+    delete g_range;
+    g_range = new faiss::RangeSearchResult(n);
+    r->index->nprobe = nprobe;
+    r->index->range_search(n, x, radius, g_range);
+    for (long i = 0; i <= n; i++) lims[i] = (long)g_range->lims[i];
+    REF_CATCH
+}
+int ref_range_results(long total, float* D, long* I) {
+    if (!g_range) return -1;
+    memcpy(D, g_range->distances, sizeof(float) * total);
+    memcpy(I, g_range->labels, sizeof(long) * total);
+    delete g_range;
+    g_range = nullptr;
+    return 0;
 }
 
 /* Error_sys::search (profile.cpp:211-227) */

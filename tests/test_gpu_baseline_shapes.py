@@ -106,7 +106,7 @@ def test_calibration_and_bounded_tc(pair):
         acc[::5] = 1.0 - eb / 2
         R.set_queries(qk, SES, q, acc, mult, stdm, profile=True)
         Dr, Ir = R.es_search(TS, SES, threads=THREADS)
-        ref_np = R.my_nprobe(TS, SES)
+        ref_np, ref_tr = R.my_nprobe(TS, SES), R.t_recalls(TS, SES)
         R.clear_my_nprobe()
         es.set_topk(qk)
         es.setparam(mult, stdm)
@@ -118,7 +118,7 @@ def test_calibration_and_bounded_tc(pair):
         assert np.array_equal(es.my_nprobe[TS:], ref_np), (mult, stdm, eb)
         assert np.array_equal(D, Dr)
         assert_results_match(D, I, Dr, Ir, what=f"bounded {mult},{stdm},{eb}")
-        assert np.array_equal(es.t_recalls[TS:], R.t_recalls(TS, SES))
+        assert np.array_equal(es.t_recalls[TS:], ref_tr)
 
 
 def test_tc_rounds_audited(pair):
@@ -189,7 +189,7 @@ def test_tc_filter_adversarial(metric, d):
             Dr, Ir = R.search_fixed(xq, K, nprobe, threads=THREADS)
             for mode in (2, 0):
                 ix.set_option("tensor_core_filter", mode)
-                ix.set_pool_budget((8 << 20) if mode == 2 else (1 << 30))  # small budget: many rounds, many thresholds
+                ix.set_pool_budget((2 << 20) if mode == 2 else (1 << 30))  # small budget: many rounds, many thresholds
                 ix.nprobe = nprobe
                 ix.set_option("tc_audit", 1 if mode == 2 else 0)
                 D, I = ix.search(xq, K)
