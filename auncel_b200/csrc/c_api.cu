@@ -379,6 +379,81 @@ int auncel_index_search(AuncelIndex* idx, int64_t n, const float* x, int64_t k, 
     API_CATCH
 }
 
+int auncel_index_set_time_model(AuncelIndex* idx, int64_t us_per_list, int64_t ns_per_code) {
+    API_TRY
+    AUNCEL_CHECK(us_per_list >= 0 && ns_per_code >= 0, "time model costs must be >= 0");
+    idx->ix.time_us_per_list = us_per_list;
+    idx->ix.time_ns_per_code = ns_per_code;
+    API_CATCH
+}
+
+int auncel_index_search_timed_device(AuncelIndex* idx, int64_t n, const float* x_dev, int64_t k,
+                                     const float* budget_ms_dev, float* distances_dev, int64_t* labels_dev) {
+    API_TRY
+    LOCK(idx);
+    QueryBatch qb;
+    qb.n = (long)n;
+    qb.x = x_dev;
+    qb.k = (int)k;
+    qb.nprobe = (int)idx->ix.nlist;  // profile.cpp:237: ix->nprobe = ix->nlist
+    qb.mode = 0;                     // time_search does not switch the tune block on (profile.cpp:229-244)
+    qb.time_tune = 1;
+    qb.require_acc = budget_ms_dev;
+    qb.D = distances_dev;
+    qb.I = (long long*)labels_dev;
+    idx->ix.search(qb);
+    API_CATCH
+}
+
+int auncel_index_search_timed(AuncelIndex* idx, int64_t n, const float* x, int64_t k, const float* budget_ms,
+                              float* distances, int64_t* labels) {
+    API_TRY
+    LOCK(idx);
+    IvfIndex& ix = idx->ix;
+    CUDA_CHECK(cudaSetDevice(ix.device));
+    AUNCEL_CHECK(k >= 1 && k <= MAX_K, "k must be in [1, 128]");
+    AUNCEL_CHECK(budget_ms != nullptr, "per-query budget missing");
+    if (n == 0) return 0;
+    cudaStream_t s = ix.stream;
+    idx->x.ensure((size_t)n * ix.d);
+    idx->D.ensure((size_t)n * k);
+    idx->I.ensure((size_t)n * k);
+    idx->acc.ensure(n);
+    h2d(idx->x.p, x, (size_t)n * ix.d * sizeof(float), s);
+    h2d(idx->acc.p, budget_ms, n * sizeof(float), s);
+    int rc = auncel_index_search_timed_device(idx, n, idx->x.p, k, idx->acc.p, idx->D.p, (int64_t*)idx->I.p);
+    if (rc != 0) return rc;
+    d2h(distances, idx->D.p, (size_t)n * k * sizeof(float), s);
+    d2h(labels, idx->I.p, (size_t)n * k * sizeof(long long), s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    API_CATCH
+}
+
+int auncel_index_range_search(AuncelIndex* idx, int64_t n, const float* x, float radius, int64_t nprobe,
+                              int64_t* lims) {
+    API_TRY
+    LOCK(idx);
+    IvfIndex& ix = idx->ix;
+    CUDA_CHECK(cudaSetDevice(ix.device));
+    AUNCEL_CHECK(lims != nullptr, "lims must hold n + 1 entries");
+    idx->x.ensure(std::max<size_t>((size_t)n * ix.d, 1));
+    h2d(idx->x.p, x, (size_t)n * ix.d * sizeof(float), ix.stream);
+    ix.range_search((long)n, idx->x.p, radius, (int)std::min<int64_t>(nprobe, ix.nlist), (long long*)lims);
+    API_CATCH
+}
+
+int auncel_index_range_search_results(AuncelIndex* idx, float* distances, int64_t* labels) {
+    API_TRY
+    LOCK(idx);
+    IvfIndex& ix = idx->ix;
+    CUDA_CHECK(cudaSetDevice(ix.device));
+    if (ix.range_total == 0) return 0;
+    if (distances) d2h(distances, ix.range_D.p, (size_t)ix.range_total * sizeof(float), ix.stream);
+    if (labels) d2h(labels, ix.range_I.p, (size_t)ix.range_total * sizeof(long long), ix.stream);
+    CUDA_CHECK(cudaStreamSynchronize(ix.stream));
+    API_CATCH
+}
+
 int auncel_index_set_error_model(AuncelIndex* idx, int n_traces, const int64_t* trace_off, const float* phi,
                                  const float* U, const float* sigma, float multipler, float std_m) {
     API_TRY
@@ -437,6 +512,7 @@ int auncel_index_search_bounded_device(AuncelIndex* idx, int64_t n, const float*
     qb.t_recalls = t_recalls_dev;
     qb.profile = flags & 1;
     qb.overhead_profile = (flags >> 1) & 1;
+    qb.time_tune = (flags >> 2) & 1;
     qb.D = distances_dev;
     qb.I = (long long*)labels_dev;
     idx->ix.search(qb);

@@ -151,6 +151,29 @@ class IndexIVFFlat:
         _ck(lib().auncel_index_search_device(self.h, x_t.shape[0], x_t.data_ptr(), k, self.nprobe, self.max_codes,
                                              D_t.data_ptr(), I_t.data_ptr()))
 
+    def range_search(self, x, radius):
+        """IndexIVF::range_search (IndexIVF.cpp:741-860) -> (lims, D, I): result of query i =
+        entries lims[i]:lims[i+1], unsorted, in scan order (RangeSearchResult)."""
+        x = _f32(x)
+        lims = np.empty(len(x) + 1, np.int64)
+        _ck(lib().auncel_index_range_search(self.h, len(x), _p(x, _f), radius, self.nprobe, _p(lims, _l)))
+        D = np.empty(int(lims[-1]), np.float32)
+        I = np.empty(int(lims[-1]), np.int64)
+        _ck(lib().auncel_index_range_search_results(self.h, _p(D, _f), _p(I, _l)))
+        return lims, D, I
+
+    def set_time_model(self, us_per_list, ns_per_code):
+        _ck(lib().auncel_index_set_time_model(self.h, int(us_per_list), int(ns_per_code)))
+
+    def search_timed(self, x, k, budget_ms):
+        """Error_sys::time_search's search (profile.cpp:229-244): latency budget per query, ms."""
+        x, budget_ms = _f32(x), _f32(budget_ms)
+        assert len(budget_ms) == len(x)
+        D = np.empty((len(x), k), np.float32)
+        I = np.empty((len(x), k), np.int64)
+        _ck(lib().auncel_index_search_timed(self.h, len(x), _p(x, _f), k, _p(budget_ms, _f), _p(D, _f), _p(I, _l)))
+        return D, I
+
     # ---- error model
     def set_error_model(self, traces, multipler=1.0, std_m=1.0):
         off = np.zeros(len(traces) + 1, np.int64)
@@ -190,7 +213,7 @@ class IndexIVFFlat:
         gt_kth = None if gt_kth is None else _f32(gt_kth)
         D = np.empty((n, max_topk), np.float32)
         I = np.empty((n, max_topk), np.int64)
-        flags = int(profile) | (int(overhead_profile) << 1)
+        flags = int(profile) | (int(overhead_profile) << 1) | (int(getattr(self, "time_tune", False)) << 2)
         _ck(lib().auncel_index_search_bounded(self.h, n, _p(x, _f), max_topk, query_topk, _p(require_acc, _f),
                                               _p(gt_kth, _f), _p(my_nprobe, _u), _p(t_recalls, _f), flags,
                                               _p(D, _f), _p(I, _l)))
@@ -262,6 +285,19 @@ class Error_sys:
         """error_pro::setparam (IVF_pro.cpp:240-256) with the two values given directly."""
         self.index.set_params(multipler, std_m)
         self.profile = False
+
+    def time_search(self, start, search_size=-1):
+        """Error_sys::time_search (profile.cpp:229-244): require_acc[id] is read as a latency budget
+        in ms; the tune block stays off.  Like the reference (:242) this leaves error_pro::time_tune
+        SET, so a later search() applies the latency cut as well until `index.time_tune = False`."""
+        if not self.is_trained:
+            raise FaissException("Error sys must be trained before searching")
+        if self.num > self.train_num:
+            raise FaissException("Error sys search num must be lower than all qeuries num")
+        n = self.num if search_size == -1 else search_size
+        sl = slice(start, start + n)
+        self.index.time_tune = True
+        return self.index.search_timed(self.queries[sl], self.max_topk, self.require_acc[sl])
 
     def search(self, start, search_size=-1):
         if not self.is_trained:  # profile.cpp:212-213

@@ -35,3 +35,7 @@ def fbin_read(fname, dtype=np.float32, max_n=None):
         if max_n is not None:
             n = min(int(n), max_n)
         return np.fromfile(f, dtype=dtype, count=int(n) * int(d)).reshape(int(n), int(d))
+
+
+def ivecs_write(fname, x):
+    fvecs_write(fname, np.ascontiguousarray(x, dtype=np.int32))

@@ -19,6 +19,8 @@
 #include <cstring>
 #include <exception>
 #include <fstream>
+#include <iostream>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <vector>
@@ -134,6 +136,30 @@ class error_pro {
     ~error_pro() { delete[] my_nprobe; delete[] t_recalls; }
 };
 
+/// AuxIndexStructures.h:31-50
+struct RangeSearchResult {
+    using idx_t = long;
+    size_t nq;
+    size_t* lims;       ///< size nq + 1: result of query i is [lims[i], lims[i+1])
+    idx_t* labels = nullptr;
+    float* distances = nullptr;  ///< not sorted
+    size_t buffer_size = 1024 * 256;
+    explicit RangeSearchResult(idx_t nq, bool alloc_lims = true) : nq((size_t)nq) {
+        lims = alloc_lims ? new size_t[nq + 1]() : nullptr;
+    }
+    /// called when lims holds the offsets (AuxIndexStructures.cpp:39-45)
+    virtual void do_allocation() {
+        size_t ofs = lims[nq];
+        labels = new idx_t[ofs];
+        distances = new float[ofs];
+    }
+    virtual ~RangeSearchResult() {
+        delete[] labels;
+        delete[] distances;
+        delete[] lims;
+    }
+};
+
 struct IndexIVF : Index {  // IndexIVF.h:97-308
     Index* quantizer;
     size_t nlist;
@@ -202,12 +228,30 @@ struct IndexIVF : Index {  // IndexIVF.h:97-308
             kth.resize(n);
             for (idx_t i = 0; i < n; i++) kth[i] = t->train_D[(offset + i) * k + t->query_topk - 1];  // IndexIVF.cpp:509
         }
-        int flags = (t->profile ? 1 : 0) | (t->overhead_profile ? 2 : 0);
+        int flags = (t->profile ? 1 : 0) | (t->overhead_profile ? 2 : 0) | (t->time_tune ? 4 : 0);
         auncel_check(auncel_index_search_bounded(h, n, x, k, (int64_t)t->query_topk, t->require_acc + offset,
                                                  kth.empty() ? nullptr : kth.data(), np.data(),
                                                  t->t_recalls ? t->t_recalls + offset : nullptr, flags, distances,
                                                  ll.data()));
         for (idx_t i = 0; i < n; i++) t->my_nprobe[offset + i] = (size_t)np[i];
+        for (size_t i = 0; i < ll.size(); i++) labels[i] = (idx_t)ll[i];
+    }
+
+    /// IndexIVF::range_search, IndexIVF.cpp:741-860
+    void range_search(idx_t nx, const float* x, float radius, RangeSearchResult* result) const {
+        std::vector<int64_t> lims((size_t)nx + 1);
+        auncel_check(auncel_index_range_search(h, nx, x, radius, (int64_t)nprobe, lims.data()));
+        for (idx_t i = 0; i <= nx; i++) result->lims[i] = (size_t)lims[i];
+        result->do_allocation();
+        static_assert(sizeof(idx_t) == sizeof(int64_t), "idx_t must be 64-bit");
+        auncel_check(auncel_index_range_search_results(h, result->distances, (int64_t*)result->labels));
+    }
+    /// the search of Error_sys::time_search (profile.cpp:229-244): latency budget per query in
+    /// t->require_acc (ms), tune block off, error_pro::time_tune cut (IndexIVF.cpp:545-549)
+    void search_timed(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels, size_t offset) const {
+        AUNCEL_FAISS_THROW_IF_NOT_MSG(t != nullptr && t->require_acc != nullptr, "set_queries was not called");
+        std::vector<int64_t> ll((size_t)n * k);
+        auncel_check(auncel_index_search_timed(h, n, x, k, t->require_acc + offset, distances, ll.data()));
         for (size_t i = 0; i < ll.size(); i++) labels[i] = (idx_t)ll[i];
     }
 
@@ -297,6 +341,16 @@ class Error_sys {
         size_t n = search_size == (size_t)-1 ? num : search_size;
         index->search((Index::idx_t)n, queries + start * index->d, (Index::idx_t)max_topk, D, (Index::idx_t*)I, start);
         index->set_tune_off();
+    }
+    /// profile.cpp:229-244.  Like the reference (:242) the flag error_pro::time_tune stays set.
+    void time_search(float* D, int64_t* I, size_t start, size_t search_size = (size_t)-1) {
+        AUNCEL_FAISS_THROW_IF_NOT_MSG(is_trained == true, "Error sys must be trained before searching");
+        AUNCEL_FAISS_THROW_IF_NOT_MSG(num <= train_num, "Error sys search num must be lower than all qeuries num");
+        index->t->time_tune = true;
+        index->nprobe = index->nlist;
+        size_t n = search_size == (size_t)-1 ? num : search_size;
+        index->search_timed((Index::idx_t)n, queries + start * index->d, (Index::idx_t)max_topk, D, (Index::idx_t*)I, start);
+        index->t->time_tune = true;
     }
 };
 
@@ -428,6 +482,116 @@ inline Index* index_factory(int d, const char* description, MetricType metric = 
     Index* quantizer = metric == METRIC_L2 ? (Index*)new IndexFlatL2(d) : (Index*)new IndexFlatIP(d);
     IndexIVFFlat* ix = new IndexIVFFlat(quantizer, d, nlist, metric);
     ix->own_fields = true;
+    return ix;
+}
+
+/// write_index / read_index (index_io.cpp:383-460, 890+) for IndexIVFFlat: the reference's "IwFl" layout --
+/// index header (:196-203), nlist, nprobe, the quantizer as "IxF2"/"IxFI" (:384-390), direct map,
+/// ArrayInvertedLists "ilar" with a "full" or "sprs" size table (:280-330) -- so files are exchangeable
+/// with the reference.  (auncel_b200/index_io.py additionally appends the Auncel state.)
+namespace io_detail {
+inline uint32_t fourcc(const char* s) { return (uint32_t)(unsigned char)s[0] | ((uint32_t)(unsigned char)s[1] << 8) | ((uint32_t)(unsigned char)s[2] << 16) | ((uint32_t)(unsigned char)s[3] << 24); }
+template <class T> inline void put(FILE* f, const T& v) { if (std::fwrite(&v, sizeof(T), 1, f) != 1) throw FaissException("write error"); }
+template <class T> inline void get(FILE* f, T& v) { if (std::fread(&v, sizeof(T), 1, f) != 1) throw FaissException("read error"); }
+inline void header(FILE* f, int d, long ntotal, bool trained, int metric) {
+    put(f, d); put(f, ntotal); long dummy = 1 << 20; put(f, dummy); put(f, dummy); put(f, trained); put(f, metric);
+}
+inline void rheader(FILE* f, int& d, long& ntotal, bool& trained, int& metric) {
+    long dummy; get(f, d); get(f, ntotal); get(f, dummy); get(f, dummy); get(f, trained); get(f, metric);
+}
+}  // namespace io_detail
+
+inline void write_index(const Index* idx, const char* fname) {
+    using namespace io_detail;
+    const IndexIVFFlat* ix = dynamic_cast<const IndexIVFFlat*>(idx);
+    AUNCEL_FAISS_THROW_IF_NOT_MSG(ix != nullptr, "write_index: only IndexIVFFlat is supported on this path");
+    const IndexFlat* fq = dynamic_cast<const IndexFlat*>(ix->quantizer);
+    AUNCEL_FAISS_THROW_IF_NOT_MSG(fq != nullptr, "the quantizer must be an IndexFlat");
+    FILE* f = std::fopen(fname, "wb");
+    if (!f) throw FaissException(std::string("could not open ") + fname + " for writing");
+    put(f, fourcc("IwFl"));
+    header(f, ix->d, ix->ntotal, ix->is_trained, (int)ix->metric_type);
+    put(f, (size_t)ix->nlist); put(f, (size_t)ix->nprobe);
+    put(f, fourcc(ix->metric_type == METRIC_L2 ? "IxF2" : "IxFI"));
+    header(f, fq->d, fq->ntotal, fq->is_trained, (int)fq->metric_type);
+    put(f, (size_t)fq->xb.size());
+    if (!fq->xb.empty() && std::fwrite(fq->xb.data(), sizeof(float), fq->xb.size(), f) != fq->xb.size()) throw FaissException("write error");
+    put(f, false); put(f, (size_t)0);  // maintain_direct_map, direct_map
+    std::vector<int64_t> sizes(ix->nlist);
+    auncel_check(auncel_index_list_sizes(ix->h, sizes.data()));
+    size_t tot = 0, nonempty = 0;
+    for (auto s : sizes) { tot += (size_t)s; nonempty += s > 0; }
+    std::vector<float> codes(tot * ix->d);
+    std::vector<int64_t> ids(tot);
+    auncel_check(auncel_index_get_lists(ix->h, codes.data(), ids.data()));
+    put(f, fourcc("ilar")); put(f, (size_t)ix->nlist); put(f, (size_t)(sizeof(float) * ix->d));
+    if (nonempty > ix->nlist / 2) {  // index_io.cpp:293-313
+        put(f, fourcc("full")); put(f, (size_t)ix->nlist);
+        for (auto s : sizes) put(f, (size_t)s);
+    } else {
+        put(f, fourcc("sprs")); put(f, (size_t)(2 * nonempty));
+        for (size_t l = 0; l < ix->nlist; l++) if (sizes[l] > 0) { put(f, l); put(f, (size_t)sizes[l]); }
+    }
+    size_t off = 0;
+    for (size_t l = 0; l < ix->nlist; l++) {
+        size_t n = (size_t)sizes[l];
+        if (n == 0) continue;
+        if (std::fwrite(codes.data() + off * ix->d, sizeof(float), n * ix->d, f) != n * ix->d) throw FaissException("write error");
+        if (std::fwrite(ids.data() + off, sizeof(int64_t), n, f) != n) throw FaissException("write error");
+        off += n;
+    }
+    std::fclose(f);
+}
+
+inline Index* read_index(const char* fname, int device = 0) {
+    using namespace io_detail;
+    FILE* f = std::fopen(fname, "rb");
+    if (!f) throw FaissException(std::string("could not open ") + fname + " for reading");
+    uint32_t h; get(f, h);
+    AUNCEL_FAISS_THROW_IF_NOT_MSG(h == fourcc("IwFl"), "read_index: only IndexIVFFlat files are supported on this path");
+    int d, metric, dq, mq; long ntotal, nq; bool trained, tq;
+    rheader(f, d, ntotal, trained, metric);
+    size_t nlist, nprobe; get(f, nlist); get(f, nprobe);
+    uint32_t hq; get(f, hq);
+    AUNCEL_FAISS_THROW_IF_NOT_MSG(hq == fourcc("IxF2") || hq == fourcc("IxFI"), "quantizer is not an IndexFlat");
+    rheader(f, dq, nq, tq, mq);
+    size_t nx; get(f, nx);
+    std::vector<float> xb(nx);
+    if (nx && std::fread(xb.data(), sizeof(float), nx, f) != nx) throw FaissException("read error");
+    bool mdm; get(f, mdm);
+    size_t ndm; get(f, ndm);
+    std::fseek(f, (long)(ndm * sizeof(long)), SEEK_CUR);
+    IndexFlat* q = metric == (int)METRIC_L2 ? (IndexFlat*)new IndexFlatL2(d) : (IndexFlat*)new IndexFlatIP(d);
+    if (nq > 0) q->add(nq, xb.data());
+    IndexIVFFlat* ix = new IndexIVFFlat(q, d, nlist, (MetricType)metric, device);
+    ix->own_fields = true;
+    ix->nprobe = nprobe;
+    uint32_t hl; get(f, hl);
+    if (hl == fourcc("ilar")) {
+        size_t nl, cs; get(f, nl); get(f, cs);
+        AUNCEL_FAISS_THROW_IF_NOT_MSG(nl == nlist && cs == sizeof(float) * d, "inverted lists do not match the index");
+        uint32_t lt; get(f, lt);
+        size_t nt; get(f, nt);
+        std::vector<size_t> tab(nt);
+        if (nt && std::fread(tab.data(), sizeof(size_t), nt, f) != nt) throw FaissException("read error");
+        std::vector<size_t> sizes(nlist, 0);
+        if (lt == fourcc("full")) sizes = tab;
+        else if (lt == fourcc("sprs")) for (size_t i = 0; i + 1 < nt; i += 2) sizes[tab[i]] = tab[i + 1];
+        else throw FaissException("unknown list type");
+        for (size_t l = 0; l < nlist; l++) {
+            size_t n = sizes[l];
+            if (n == 0) continue;
+            std::vector<float> codes(n * d);
+            std::vector<long> ids(n), ln(n, (long)l);
+            if (std::fread(codes.data(), sizeof(float), n * d, f) != n * d) throw FaissException("read error");
+            if (std::fread(ids.data(), sizeof(long), n, f) != n) throw FaissException("read error");
+            ix->add_core((Index::idx_t)n, codes.data(), ids.data(), ln.data());
+        }
+        ix->ntotal = ntotal;
+    } else {
+        AUNCEL_FAISS_THROW_IF_NOT_MSG(hl == fourcc("il00"), "unsupported inverted lists");
+    }
+    std::fclose(f);
     return ix;
 }
 

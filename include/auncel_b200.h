@@ -128,7 +128,9 @@ int auncel_index_calibrate(AuncelIndex* idx, int64_t n, const float* x, int64_t 
  *   gt_kth       n ground-truth distances at rank query_topk-1, or NULL (only `profile`)
  *   my_nprobe    n, in/out: error_pro::my_nprobe[id] (0 = undecided on input)
  *   t_recalls    n, in/out, or NULL: error_pro::t_recalls[id]
- *   flags        bit 0 = error_pro::profile, bit 1 = error_pro::overhead_profile */
+ *   flags        bit 0 = error_pro::profile, bit 1 = error_pro::overhead_profile,
+ *                bit 2 = error_pro::time_tune (the flag Error_sys::time_search leaves set, profile.cpp:242:
+ *                require_acc is then ALSO read as a latency budget in ms, IndexIVF.cpp:545-549) */
 int auncel_index_search_bounded(AuncelIndex* idx, int64_t n, const float* x, int64_t max_topk,
                                 int64_t query_topk, const float* require_acc,
                                 const float* gt_kth, uint64_t* my_nprobe, float* t_recalls,
@@ -138,6 +140,30 @@ int auncel_index_search_bounded_device(AuncelIndex* idx, int64_t n, const float*
                                        const float* require_acc_dev, const float* gt_kth_dev,
                                        uint64_t* my_nprobe_dev, float* t_recalls_dev, int flags,
                                        float* distances_dev, int64_t* labels_dev);
+
+/* Error_sys::time_search (profile.cpp:229-244): nprobe = nlist, no tune block; after every probed
+ * list the reference breaks when  elapsed_ms >= 0.95 * budget_ms - elapsed_ms / lists_done
+ * (IndexIVF.cpp:545-549, IndexIVF::time() = gettimeofday :329-333).  On the device the clock is a
+ * MODEL, so the cut is deterministic: every probe iteration costs us_per_list microseconds plus
+ * ns_per_code nanoseconds per code of the list; time() is evaluated on the resulting (tv_sec,
+ * tv_usec) pair with the reference's double arithmetic.  budget_ms: n values (what the reference
+ * keeps in require_acc[id] in this mode).  Default model: 2 us per list, 0 ns per code. */
+int auncel_index_set_time_model(AuncelIndex* idx, int64_t us_per_list, int64_t ns_per_code);
+int auncel_index_search_timed(AuncelIndex* idx, int64_t n, const float* x, int64_t k,
+                              const float* budget_ms, float* distances, int64_t* labels);
+int auncel_index_search_timed_device(AuncelIndex* idx, int64_t n, const float* x_dev, int64_t k,
+                                     const float* budget_ms_dev, float* distances_dev,
+                                     int64_t* labels_dev);
+
+/* IndexIVF::range_search (IndexIVF.cpp:741-860, scan_codes_range IndexIVFFlat.cpp:139-155): all
+ * vectors of the nprobe nearest lists with dis < radius (L2) / dis > radius (inner product).
+ * Two calls, like RangeSearchResult (AuxIndexStructures.h:31-50): the first searches and fills
+ * lims[n + 1] (result of query i = entries lims[i] .. lims[i+1]); the caller allocates lims[n]
+ * entries (do_allocation) and the second call copies distances / labels, in the reference's scan
+ * order (probe rank, then in-list order).  The results of a search are kept until the next one. */
+int auncel_index_range_search(AuncelIndex* idx, int64_t n, const float* x, float radius,
+                              int64_t nprobe, int64_t* lims);
+int auncel_index_range_search_results(AuncelIndex* idx, float* distances, int64_t* labels);
 
 /* IndexIVFStats (IndexIVF.h:361-374) of the last search on this index + engine counters.
  * out[0]=nq [1]=nlist visited [2]=ndis [3]=search ms (device) [4]=rounds [5]=scan tiles

@@ -311,8 +311,14 @@ class RefIndex:
                                         len(acc), multipler, std_m, int(profile),
                                         int(overhead_profile)))
 
-    def es_search(self, start, num, search_size=-1, threads=0):
+    def es_search(self, start, num, search_size=-1, threads=0, virtual_clock=False):
         """search_size=-1: one batched call over `num` queries; 1: the eval/bound.cpp loop."""
+        if virtual_clock:  # error_pro::time_tune left set by time_search: the cut needs the test clock
+            self.lib.ref_set_virtual_clock(1)
+            try:
+                return self.es_search(start, num, search_size, threads)
+            finally:
+                self.lib.ref_set_virtual_clock(0)
         k = self.max_topk
         D = np.empty((num, k), np.float32)
         I = np.empty((num, k), np.int64)
@@ -326,7 +332,7 @@ class RefIndex:
                 _ck(self.lib.ref_es_search(self.h, _p(D[q:], _f), _p(I[q:], _l), start + q, m))
         return D, I
 
-    def es_time_search(self, start, num, virtual_clock=True):
+    def es_time_search(self, start, num, virtual_clock=True, keep_flag=False):
         """Error_sys::time_search (profile.cpp:229-244); require_acc = budget in ms.  With the
         virtual clock every IndexIVF::time() call advances by exactly 1 s (ref_driver.cpp)."""
         k = self.max_topk
@@ -334,7 +340,7 @@ class RefIndex:
         I = np.empty((num, k), np.int64)
         self.lib.ref_set_virtual_clock(int(virtual_clock))
         try:
-            _ck(self.lib.ref_es_time_search(self.h, _p(D, _f), _p(I, _l), start, num, 1))
+            _ck(self.lib.ref_es_time_search(self.h, _p(D, _f), _p(I, _l), start, num, 0 if keep_flag else 1))
         finally:
             self.lib.ref_set_virtual_clock(0)
         return D, I
@@ -575,7 +581,7 @@ class OracleIndex:
         return D, I
 
     def search_bounded(self, x, max_topk, query_topk, require_acc, gt_D=None, offset=0,
-                       my_nprobe=None, profile=False, overhead_profile=False, dump_q=-1):
+                       my_nprobe=None, profile=False, overhead_profile=False, dump_q=-1, time_model=None):
         """Error_sys::search (profile.cpp:211-227): nprobe = nlist, tune block on.
         require_acc / gt_D / my_nprobe are indexed by GLOBAL id (offset + i)."""
         x = f32(x)
@@ -584,8 +590,13 @@ class OracleIndex:
         if my_nprobe is None:
             my_nprobe = np.zeros(offset + n, np.uint64)
         t_rec = np.zeros(offset + n, np.float32)
-        D, I = self.search_preassigned(x, max_topk, keys, dis, mode=1, offset=offset,
-                                       query_topk=query_topk, require_acc=require_acc, gt_D=gt_D,
-                                       profile=profile, overhead_profile=overhead_profile,
-                                       my_nprobe=my_nprobe, t_recalls=t_rec, dump_q=dump_q)
+        if time_model is not None:  # error_pro::time_tune still set (profile.cpp:242)
+            self.lib.orc_set_time_tune(1, int(time_model[0]), int(time_model[1]))
+        try:
+            D, I = self.search_preassigned(x, max_topk, keys, dis, mode=1, offset=offset,
+                                           query_topk=query_topk, require_acc=require_acc, gt_D=gt_D,
+                                           profile=profile, overhead_profile=overhead_profile,
+                                           my_nprobe=my_nprobe, t_recalls=t_rec, dump_q=dump_q)
+        finally:
+            self.lib.orc_set_time_tune(0, 0, 0)
         return D, I, my_nprobe, t_rec

@@ -126,3 +126,66 @@ def test_bounded_search_live(metric, d, nb, k, qk, seed):
         assert np.array_equal(trec[ts:], R.t_recalls(ts, ses))
         R.clear_my_nprobe()
     R.close()
+
+
+@pytest.mark.parametrize("metric", [O.L2, O.IP])
+def test_range_search_live(metric):
+    """IndexIVF::range_search (IndexIVF.cpp:741-860): lims, distances and labels, in scan order."""
+    O.RefIndex.set_blas_threshold(1 << 30)
+    d, nlist, nb = 20, 64, 8000
+    norm = metric == O.IP
+    xb = synth.clustered(3, nb, d, 40, normalize=norm)
+    xq = synth.clustered(9, 45, d, 40, normalize=norm)
+    R = O.RefIndex(d, nlist, metric)
+    R.train(xb, niter=2)
+    R.add(xb)
+    orc = O.OracleIndex(d, nlist, metric)
+    orc.set_centroids(R.centroids())
+    orc.add(xb)
+    gD, _ = R.search_fixed(xq, 20, nlist)
+    for col in (0, 3, 19):
+        rad = float(np.median(gD[:, col]))
+        for nprobe in (1, 9, nlist):
+            l1, D1, I1 = R.range_search(xq, rad, nprobe)
+            l2, D2, I2 = orc.range_search(xq, rad, nprobe)
+            assert np.array_equal(l1, l2) and np.array_equal(D1, D2) and np.array_equal(I1, I2)
+    assert l1[-1] > 0
+    R.close()
+
+
+def test_time_search_live():
+    """Error_sys::time_search (profile.cpp:229-244) under the test clock (every IndexIVF::time()
+    call = +1 s, ref_driver.cpp) against the restatement's clock model (1e6 us per list): the cut of
+    IndexIVF.cpp:545-549 -- and the reference leaving error_pro::time_tune set afterwards (:242), so
+    that the NEXT tuned search is cut as well."""
+    O.RefIndex.set_blas_threshold(1 << 30)
+    d, nlist, nb, k, qk = 16, 1024, 30000, 10, 4
+    xb = synth.clustered(3, nb, d, 300)
+    xq = synth.clustered(9, 60, d, 300)
+    R = O.RefIndex(d, nlist, O.L2)
+    R.train(xb, niter=2)
+    R.add(xb)
+    orc = O.OracleIndex(d, nlist, O.L2)
+    orc.set_centroids(R.centroids())
+    orc.add(xb)
+    gD, gI = R.search_fixed(xq, k, nlist)
+    R.es_create(gD, gI)
+    R.sys_train(30, xq)
+    orc.calibrate(xq[:30], gD[:30])
+    bud = np.array([(i % 11 + 2) * 1300.0 for i in range(60)], np.float32)  # "ms" of the 1 s/call clock
+    R.set_queries(qk, 30, xq, bud, 1.0, 1.0)
+    D, I = R.es_time_search(30, 30, keep_flag=True)
+    D2, I2 = orc.search_timed(xq[30:], k, bud, 1_000_000, 0, offset=30)
+    assert np.array_equal(D, D2) and np.array_equal(I, I2)
+    assert not np.array_equal(D, gD[30:])  # the budget did cut the scan
+    # sticky flag: a tuned search now reads require_acc both as recall target and as budget
+    acc = np.full(60, 0.9, np.float32)
+    acc[::2] = 4000.0  # every other query: a target no recall estimate reaches -> only the time cut stops it
+    R.set_queries(qk, 30, xq, acc, 2.0, 1.0)
+    D, I = R.es_search(30, 30, virtual_clock=True)
+    orc.multipler, orc.std_m = 2.0, 1.0
+    D2, I2, mynp, _ = orc.search_bounded(xq[30:], k, qk, acc, gt_D=gD, offset=30, time_model=(1_000_000, 0))
+    assert np.array_equal(D, D2) and np.array_equal(I, I2)
+    assert np.array_equal(mynp[30:], R.my_nprobe(30, 30))
+    O.ref().ref_es_time_search  # (flag reset for later users of this handle)
+    R.close()
