@@ -77,9 +77,10 @@ def test_fixed_nprobe_tc(pair, nprobe):
     D, I = ix.search(q[TS:], c["K"])
     st = ix.stats()
     assert st["tc_rounds"] > 0, st
-    Dr, Ir = R.search_fixed(q[TS:], c["K"], nprobe, threads=THREADS)
+    Dr, Ir = R.search_fixed(q[TS:], c["K"] + 1, nprobe, threads=THREADS)
+    Dn, Dr, Ir = Dr[:, -1], np.ascontiguousarray(Dr[:, :-1]), np.ascontiguousarray(Ir[:, :-1])
     assert np.array_equal(D, Dr)
-    assert_results_match(D, I, Dr, Ir, what=f"fixed nprobe={nprobe}")
+    assert_results_match(D, I, Dr, Ir, what=f"fixed nprobe={nprobe}", D_next=Dn)
     assert (I == Ir).mean() > 0.999
 
 
@@ -186,7 +187,8 @@ def test_tc_filter_adversarial(metric, d):
         R.set_centroids(cent)
         R.add(xb, ids=np.arange(len(xb), dtype=np.int64), list_no=ix.assign(xb))
         for nprobe in (12, 48):
-            Dr, Ir = R.search_fixed(xq, K, nprobe, threads=THREADS)
+            Dr, Ir = R.search_fixed(xq, K + 1, nprobe, threads=THREADS)  # one extra column: ties at the k-th edge
+            Dn, Dr, Ir = Dr[:, K], np.ascontiguousarray(Dr[:, :K]), np.ascontiguousarray(Ir[:, :K])
             for mode in (2, 0):
                 ix.set_option("tensor_core_filter", mode)
                 ix.set_pool_budget((2 << 20) if mode == 2 else (1 << 30))  # small budget: many rounds, many thresholds
@@ -196,9 +198,9 @@ def test_tc_filter_adversarial(metric, d):
                 st = ix.stats()
                 assert st["tc_audit_bad"] == 0, (name, nprobe, st)
                 assert np.array_equal(D, Dr), (name, nprobe, mode, st)
-                assert_results_match(D, I, Dr, Ir, what=f"{name} nprobe={nprobe} tc={mode}")
+                assert_results_match(D, I, Dr, Ir, what=f"{name} nprobe={nprobe} tc={mode}", D_next=Dn)
                 if mode == 2:
-                    assert st["tc_rounds"] + st["tc_fallbacks"] > 0, (name, st)
+                    assert st["rounds"] > 1 and st["tc_rounds"] + st["tc_fallbacks"] > 0, (name, st)
                     used_tc += st["tc_rounds"] > 0
         R.close()
         del ix

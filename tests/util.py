@@ -39,9 +39,11 @@ def golden_traces(g):
             for t in range(int(g["n_traces"]))]
 
 
-def assert_results_match(D, I, Dref, Iref, rtol_d=1e-4, tie_rtol=1e-5, what=""):
+def assert_results_match(D, I, Dref, Iref, rtol_d=1e-4, tie_rtol=1e-5, what="", D_next=None):
     """north_star tolerance: distances within 1e-4 relative; ids identical except where
-    the reference row has another entry within 1e-5 relative (a tie)."""
+    the reference row has another entry within 1e-5 relative (a tie).  D_next (optional, one
+    value per row): the reference's NEXT distance after the row's last one -- a tie between the
+    k-th and the (k+1)-th neighbour is a tie too, it just is not visible inside the row."""
     D, Dref = np.asarray(D, np.float64), np.asarray(Dref, np.float64)
     assert D.shape == Dref.shape, what
     big = np.abs(Dref) > 1e37
@@ -54,7 +56,9 @@ def assert_results_match(D, I, Dref, Iref, rtol_d=1e-4, tie_rtol=1e-5, what=""):
         for r, c in zip(rows, cols):
             row = Dref[r]
             near = np.abs(row - row[c]) <= tie_rtol * max(abs(row[c]), 1e-30)
-            assert near.sum() > 1 or big[r, c], f"{what}: id mismatch at ({r},{c}) not a tie"
+            edge = D_next is not None and abs(float(D_next[r]) - row[c]) <= tie_rtol * max(abs(row[c]), 1e-30)
+            assert near.sum() > 1 or big[r, c] or edge, (f"{what}: id mismatch at ({r},{c}) not a tie: ours {I[r][c]} ref {Iref[r][c]} "
+                                                        f"D {row[max(0, c - 2):c + 2]} next {None if D_next is None else D_next[r]}")
 
 
 def recall_at(gt_D, D, qk, metric):
