@@ -63,6 +63,13 @@ SYMBOLS = {
     "auncel_heap_entry_table": (C.c_int, [C.c_int64, C.POINTER(C.c_int32)]),
     "auncel_merge_tables_device": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "auncel_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "auncel_shard_group_new": (C.c_int, [C.POINTER(_h), _h, C.c_int, C.c_int, C.c_void_p]),
+    "auncel_shard_group_free": (None, [_h]),
+    "auncel_shard_group_search": (C.c_int, [_h, C.c_int64, _f, C.c_int64, C.c_int64, C.c_int64, _f, _l]),
+    "auncel_shard_group_search_device": (C.c_int, [_h, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                                   C.c_void_p, C.c_void_p]),
+    "auncel_shard_group_get_stats": (C.c_int, [_h, _d]),
     "auncel_index_copy_subset_to": (C.c_int, [_h, _h, C.c_int, C.c_int64, C.c_int64]),
 }
 

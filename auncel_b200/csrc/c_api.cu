@@ -26,6 +26,8 @@ struct AuncelIndex_H {
 #define LOCK(idx) std::lock_guard<std::recursive_mutex> lock_((idx)->mu)
 
 static thread_local std::string g_last_error;
+void auncel_set_last_error(const std::string& m) { g_last_error = m; }          // shards.cu
+auncel::IvfIndex* auncel_index_engine(AuncelIndex* idx) { return &idx->ix; }    // shards.cu
 
 #define API_TRY try {
 #define API_CATCH                                           \

@@ -232,6 +232,9 @@ void launch_merge_tables(int metric, long n, long k, long nshard, const float* a
                          const long long* all_I, const long long* translations, float* D,
                          long long* I, cudaStream_t s);
 
+void launch_merge_tables_strided(int metric, long n, long k, long nshard, const float* all_D, const long long* all_I,
+                                 long stride_D, long stride_I, const long long* translations, float* D, long long* I,
+                                 cudaStream_t s);
 // Index::train: k-means on the device (kmeans.cu), then set_centroids
 void train_kmeans(IvfIndex& ix, long nx, const float* x_host, int niter, bool tune);
 

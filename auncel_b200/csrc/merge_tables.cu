@@ -23,21 +23,21 @@ __device__ __forceinline__ bool mt_cmp(float a, float b) {  // C::cmp of the mer
 
 template <int METRIC>
 __global__ void merge_tables_kernel(long n, int k, int nshard, const float* __restrict__ all_D,
-                                    const long long* __restrict__ all_I, const long long* __restrict__ tr,
-                                    float* __restrict__ D, long long* __restrict__ I) {
+                                    const long long* __restrict__ all_I, long stride_D, long stride_I,
+                                    const long long* __restrict__ tr, float* __restrict__ D,
+                                    long long* __restrict__ I) {
     extern __shared__ __align__(8) unsigned char mt_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const size_t per_warp = (size_t)nshard * k + k + MAX_SHARDS;  // 4-byte words
     float* sD = reinterpret_cast<float*>(mt_smem) + warp * per_warp;
     unsigned* sOut = reinterpret_cast<unsigned*>(sD + (size_t)nshard * k);  // (shard << 24) | position, or ~0u
     int* sLen = reinterpret_cast<int*>(sOut + k);
-    const long stride = n * (long)k;
     for (long q = blockIdx.x * (long)wpb + warp; q < n; q += (long)gridDim.x * wpb) {
         for (int s = 0; s < nshard; s++) {
             int first_neg = k;
             for (int p = lane; p < k; p += 32) {
-                sD[s * k + p] = all_D[stride * s + q * k + p];
-                if (all_I[stride * s + q * k + p] < 0) first_neg = min(first_neg, p);
+                sD[s * k + p] = all_D[stride_D * s + q * k + p];
+                if (all_I[stride_I * s + q * k + p] < 0) first_neg = min(first_neg, p);
             }
             for (int o = 16; o > 0; o >>= 1) first_neg = min(first_neg, __shfl_xor_sync(0xffffffffu, first_neg, o));
             if (lane == 0) sLen[s] = first_neg;
@@ -107,7 +107,7 @@ __global__ void merge_tables_kernel(long n, int k, int nshard, const float* __re
             } else {
                 const int s = (int)(o >> 24), p = (int)(o & 0xffffffu);
                 D[q * k + j] = sD[s * k + p];
-                I[q * k + j] = all_I[stride * s + q * k + p] + (tr ? tr[s] : 0);
+                I[q * k + j] = all_I[stride_I * s + q * k + p] + (tr ? tr[s] : 0);
             }
         }
         __syncwarp();
@@ -116,6 +116,14 @@ __global__ void merge_tables_kernel(long n, int k, int nshard, const float* __re
 
 void launch_merge_tables(int metric, long n, long k, long nshard, const float* all_D, const long long* all_I,
                          const long long* translations, float* D, long long* I, cudaStream_t s) {
+    launch_merge_tables_strided(metric, n, k, nshard, all_D, all_I, n * k, n * k, translations, D, I, s);
+    if (s == nullptr) CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+// shard s's tables start at all_D + s * stride_D / all_I + s * stride_I (elements)
+void launch_merge_tables_strided(int metric, long n, long k, long nshard, const float* all_D, const long long* all_I,
+                                 long stride_D, long stride_I, const long long* translations, float* D, long long* I,
+                                 cudaStream_t s) {
     AUNCEL_CHECK(nshard >= 1 && nshard <= MAX_SHARDS, "nshard must be in [1, 64]");
     AUNCEL_CHECK(k < (1 << 24), "k too large");
     if (n == 0 || k == 0) return;
@@ -126,9 +134,8 @@ void launch_merge_tables(int metric, long n, long k, long nshard, const float* a
     auto kern = metric == METRIC_L2 ? merge_tables_kernel<METRIC_L2> : merge_tables_kernel<METRIC_IP>;
     if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (unsigned)std::min<long>((n + wpb - 1) / wpb, 148L * 16);
-    kern<<<blocks, wpb * 32, smem, s>>>(n, (int)k, (int)nshard, all_D, all_I, translations, D, I);
+    kern<<<blocks, wpb * 32, smem, s>>>(n, (int)k, (int)nshard, all_D, all_I, stride_D, stride_I, translations, D, I);
     CUDA_CHECK(cudaGetLastError());
-    if (s == nullptr) CUDA_CHECK(cudaStreamSynchronize(s));
 }
 
 }  // namespace auncel

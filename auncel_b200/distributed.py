@@ -100,7 +100,84 @@ class _EsAdapter:
         I_t.copy_(self.tables[1])
 
 
+class NcclShardGroup:
+    """IndexShards over GPUs inside the library (csrc/shards.cu): local search, ONE ncclAllGather of the
+    packed (distances | labels) table on the index stream, merge_tables behind it.  torch.distributed
+    only carries the 128-byte NCCL unique id from rank 0 to the other ranks at construction."""
+
+    def __init__(self, index, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from ._lib import lib
+        from .index import _ck
+        self.index = index
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.world > 1:
+            if self.rank == 0:
+                buf = (C.c_uint8 * 128)()
+                _ck(lib().auncel_nccl_unique_id(buf))
+                uid = torch.tensor(list(buf), dtype=torch.uint8)
+            dev = torch.device("cuda", index.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            uid = uid.to(dev)
+            dist.broadcast(uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            uid = uid.cpu()
+        raw = (C.c_uint8 * 128)(*uid.tolist())
+        h = C.c_void_p()
+        _ck(lib().auncel_shard_group_new(C.byref(h), index.h, self.rank, self.world, raw))
+        self.h = h
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            from ._lib import lib
+            lib().auncel_shard_group_free(h)
+
+    def search_device(self, x_t, k, D_t=None, I_t=None):
+        """x_t: (n, d) CUDA tensor, identical on every rank.  Every rank gets the merged (n, k) tables."""
+        import torch
+
+        from ._lib import lib
+        from .index import _ck
+        n = x_t.shape[0]
+        if D_t is None:
+            D_t = torch.empty(n, k, device=x_t.device, dtype=torch.float32)
+            I_t = torch.empty(n, k, device=x_t.device, dtype=torch.int64)
+        self.index._after(x_t)
+        _ck(lib().auncel_shard_group_search_device(self.h, n, x_t.data_ptr(), k, self.index.nprobe,
+                                                   self.index.max_codes, D_t.data_ptr(), I_t.data_ptr()))
+        return D_t, I_t
+
+    def search(self, x, k):
+        import numpy as np
+
+        from ._lib import _f, _l, lib
+        from .index import _ck, _f32, _p
+        x = _f32(x)
+        D = np.empty((len(x), k), np.float32)
+        I = np.empty((len(x), k), np.int64)
+        _ck(lib().auncel_shard_group_search(self.h, len(x), _p(x, _f), k, self.index.nprobe, self.index.max_codes,
+                                            _p(D, _f), _p(I, _l)))
+        return D, I
+
+    def stats(self):
+        import ctypes as C
+
+        from ._lib import lib
+        out = (C.c_double * 8)()
+        lib().auncel_shard_group_get_stats(self.h, out)
+        return dict(zip(["local_ms", "allgather_ms", "merge_ms", "allgather_bytes", "world", "rank", "nccl_version"],
+                        [float(v) for v in out]))
+
+
 class ShardGroup:
+    """The same semantics with torch.distributed doing the gather (any backend): what the CPU tests drive
+    with a recording mock over gloo, and what BoundedShardGroup builds on."""
+
     def __init__(self, index, metric, group=None, translations=None, merge_fn=None, device=None):
         import torch.distributed as dist
         self.index, self.metric, self.group, self.dist = index, metric, group, dist

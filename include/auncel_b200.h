@@ -197,6 +197,30 @@ int auncel_merge_tables_device(int device, int metric, int64_t n, int64_t k, int
                                const int64_t* translations_dev, float* distances_dev,
                                int64_t* labels_dev, void* cuda_stream);
 
+/* ---- IndexShards over GPUs, one process per GPU (IndexShards.cpp:261-311 + merge_tables :44-105) ----
+ * Every rank holds one shard: an AuncelIndex with the SHARED centroids and its slice of every inverted
+ * list (copy_subset_to below, or add_with_ids of the rank's vectors).  A search runs the local
+ * fixed-nprobe search of all n queries, ONE ncclAllGather of the packed (n x k distances | n x k labels)
+ * table on the index stream, and merge_tables behind it on the same stream; every rank returns the
+ * merged (n x k) tables, equal to the unsharded index (tests/test_merge.cpp:94-152 invariant).
+ * Setup: rank 0 calls auncel_nccl_unique_id and hands the 128 bytes to all ranks by any means (MPI,
+ * torch.distributed, a file); every rank then calls auncel_shard_group_new (collective: ncclCommInitRank).
+ * NCCL is loaded at run time (the libnccl.so.2 already in the process, else the system's; override with
+ * AUNCEL_NCCL_LIB); world == 1 needs neither an id nor NCCL. */
+typedef struct AuncelShardGroup_H AuncelShardGroup;
+int auncel_nccl_unique_id(void* out128);
+int auncel_shard_group_new(AuncelShardGroup** out, AuncelIndex* local_shard, int rank, int world,
+                           const void* nccl_id128);
+void auncel_shard_group_free(AuncelShardGroup* g);
+int auncel_shard_group_search(AuncelShardGroup* g, int64_t n, const float* x, int64_t k, int64_t nprobe,
+                              int64_t max_codes, float* distances, int64_t* labels);
+int auncel_shard_group_search_device(AuncelShardGroup* g, int64_t n, const float* x_dev, int64_t k,
+                                     int64_t nprobe, int64_t max_codes, float* distances_dev,
+                                     int64_t* labels_dev);
+/* last call: out[0] local search ms, [1] all-gather ms, [2] merge ms (CUDA events on the index stream),
+ * [3] bytes received by the all-gather, [4] world, [5] rank, [6] NCCL version code */
+int auncel_shard_group_get_stats(const AuncelShardGroup* g, double* out8);
+
 /* IndexIVF::copy_subset_to (IndexIVF.cpp:1055-1118): append to `other` (same centroids) the
  * entries selected by subset_type 1 (id % a1 == a2) or 2 (proportional in-list slice a1..a2
  * of ntotal).  This is how an index is split across GPUs (gpu/GpuAutoTune.cpp:201-220). */

@@ -43,6 +43,20 @@ def _worker(rank, world, port, out):
         torch.cuda.synchronize()
         assert np.array_equal(D.cpu().numpy(), Dref)
         assert (I.cpu().numpy() == Iref).mean() > 0.999
+        # the same inside the library: ncclAllGather of the packed tables + merge on the index stream
+        nsg = AD.NcclShardGroup(shard)
+        for kk, npb in [(k, 6), (100, 17), (1, 1)]:
+            full.nprobe = shard.nprobe = npb
+            Dr_k, Ir_k = full.search(xq, kk)
+            D2, I2 = nsg.search_device(xq_t, kk)
+            assert np.array_equal(D2.cpu().numpy(), Dr_k)
+            assert (I2.cpu().numpy() == Ir_k).mean() > 0.999
+            D3, I3 = nsg.search(xq, kk)  # host-pointer entry point
+            assert np.array_equal(D3, Dr_k) and np.array_equal(I3, I2.cpu().numpy())
+            st = nsg.stats()
+            assert st["world"] == world and st["allgather_bytes"] == world * (((300 * kk * 4 + 7) // 8) * 8 + 300 * kk * 8)
+            assert st["nccl_version"] > 0
+        full.nprobe = shard.nprobe = 6
         # replicas
         rg = AD.ReplicaGroup(full)
         base, Dr, Ir = rg.search(xq, k)

@@ -195,6 +195,21 @@ def test_merge_tables_tie_order(metric, nshard, k):
     assert np.array_equal(I, I2)
 
 
+def test_shard_group_world_of_one():
+    """auncel_shard_group_* with a single shard: no NCCL, the packed table goes straight to the merge."""
+    from auncel_b200 import distributed as AD
+    d, nlist, nb, k = 16, 32, 4000, 10
+    xb, cent, orc, ix = build_pair(O.L2, d, nlist, nb)
+    xq = synth.clustered(31, 50, d)
+    ix.nprobe = 4
+    Df, If = ix.search(xq, k)
+    g = AD.NcclShardGroup(ix)
+    D, I = g.search(xq, k)
+    assert np.array_equal(D, Df) and np.array_equal(I, If)
+    st = g.stats()
+    assert st["world"] == 1 and st["allgather_bytes"] == 50 * k * 12
+
+
 def test_train_kmeans_runs_and_searches():
     d, nlist = 16, 64
     xb = synth.clustered(41, 20000, d, 30)
