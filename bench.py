@@ -3,9 +3,9 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (configs[1] of BASELINE.json): IVF-Flat nlist=4096, 10M x 128 synthetic SIFT-shaped
-base, 10k test queries (+5k calibration queries), result heap max_topk=100, query_topk=10,
-error bound 0.1 (targets 0.05 / 0.2 are timed once each and reported under "error_bounds").
+Headline workload (configs[1] of BASELINE.json): IVF-Flat nlist=4096, 10M x 128 synthetic
+SIFT-shaped base, 10k test queries (+5k calibration queries), result heap max_topk=100,
+query_topk=10, error bound 0.1 (0.05 / 0.2 are timed once each under "error_bounds").
 One step = one Error_sys::search over the whole query batch.
   value  : queries/s with the queries already resident in HBM (device C-ABI entry point)
   e2e    : queries/s through the host-pointer C-ABI call (pinned host buffers; H2D of the
@@ -13,8 +13,18 @@ One step = one Error_sys::search over the whole query batch.
 N > 1 (torchrun, one rank per GPU): replicas -- IndexReplicas semantics
 (Auncel/IndexReplicas.cpp:79-118): every rank holds the index and serves its own query batch,
 no data-path collective; value = all ranks' queries / max-over-ranks time ("weak").
---impl reference: the unmodified reference (oracle/_ref, all host threads) on a bounded
-sample of the same workload, rank 0 only.
+
+Explanatory sections of the same JSON line (none of them changes `value`):
+  roofline     dominant kernel (tc_filter_kernel): fraction of the ACTIVE bound -- compulsory (unique)
+               HBM bytes per launch / launch time against the measured copy peak, or TF32 rate against
+               the measured tensor peak, chosen by arithmetic intensity; step-level floor
+  hbm_bound    the regime where "fraction of HBM peak" is defined: batch 1 and 64 on the
+               headline index and on config 4's TEXT shape (10M x 200, normalised inner product)
+  shards       config 3: 10M x 96 DEEP-shaped inner product, k = 100, fixed nprobe, the inverted lists
+               split over the N ranks (id % N), ncclAllGather of the packed tables + merge inside the
+               library (IndexShards.cpp:261-311); strong scaling; result compared with the unsharded index
+  cpu_baseline the unmodified reference (oracle/_ref) on all host threads, bounded sample
+--impl reference: that reference arm alone, rank 0 only.
 """
 import argparse
 import json
@@ -46,16 +56,18 @@ def isolate_stdout():
     sys.stdout.flush()
     _JSON_OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
+
+
 sys.path.insert(0, ROOT)
 
 QUERY_TOPK = 10
-# dram__bytes_read.sum + dram__bytes_write.sum per tc_filter launch, mean of the four launches of one
-# default step under ncu (profiles/r01_tc_traffic.txt: 5.48 + 7.26 + 5.73 + 3.16 GB in 4.42 ms)
-TC_TRAFFIC_PER_LAUNCH = 5.40e9
 MAX_TOPK = 100
 # (multipler, std_m) per error bound: Auncel/hyperparameter.txt lines 6 / 7 are the authors'
 # SIFT10M k=10 settings for eb=0.1 / 0.05 (eval/run.sh:13-15); eb=0.2 reuses line 6.
 HYPER = {0.1: (7.9, 6.0), 0.05: (10.2, 6.0), 0.2: (7.9, 6.0)}
+# dram__bytes_read.sum + dram__bytes_write.sum per tc_filter launch of the default step under ncu
+# (profiles/r02_tc_traffic.txt, refreshed whenever the kernel changes); None = not measured for this build
+TC_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_tc_traffic.json")
 
 
 def parse():
@@ -72,6 +84,8 @@ def parse():
     ap.add_argument("--eb", type=float, default=0.1)
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the hbm_bound / shards sections")
+    ap.add_argument("--shards-nprobe", type=int, default=64)
     return ap.parse_args()
 
 
@@ -120,34 +134,169 @@ class ClockSampler:
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        mp = json.load(open(p))
+        return dict(hbm=mp["hbm_gbs"], tf32=mp.get("bf16_tflops", 0) / 2.0 or None,
+                    tf32_sustained=mp.get("bf16_tflops_sustained", 0) / 2.0 or None,
+                    source="measured (MEASURED_PEAKS.json: hbm_gbs; tf32 = bf16_tflops / 2)")
+    return dict(hbm=6650.0, tf32=None, tf32_sustained=None, source="fallback (B200_PROFILING.md)")
 
 
-def build_everything(a, dev_index, rank):
+def build_everything(a, dev_index, rank, shape=None, nlist=None, calibrate=True):
     """Synthetic base + queries on the device, index build, exact ground truth, calibration."""
     import torch
 
     import auncel_b200 as ab
     from auncel_b200 import workload as W
+    shape = shape or a.shape
+    nlist = nlist or a.nlist
     dev = torch.device(f"cuda:{dev_index}")
     t0 = time.time()
-    base = W.make_vectors(a.shape, a.nb, 123, dev)
+    base = W.make_vectors(shape, a.nb, 123, dev)
     # queries: calibration set shared by all ranks, test set per rank (replicas serve different queries)
-    qcal = W.make_vectors(a.shape, a.ncal, 456, dev)
-    qtest = W.make_vectors(a.shape, a.nq, 789 + rank, dev)
-    ix = W.build_index(ab, a.shape, base, a.nlist, dev_index, niter=10)
+    qcal = W.make_vectors(shape, a.ncal, 456, dev)
+    qtest = W.make_vectors(shape, a.nq, 789 + rank, dev)
+    ix = W.build_index(ab, shape, base, nlist, dev_index, niter=10)
     q_all = torch.cat([qcal, qtest])
     gD, gI = W.ground_truth(ix, q_all, MAX_TOPK)
     es = ab.Error_sys(ix, a.ncal + a.nq, MAX_TOPK)
     gD_h = gD.cpu().numpy()
     es.set_gt(gD_h, gI.cpu().numpy())
-    es.sys_train(a.ncal, qcal.cpu().numpy())
+    if calibrate:
+        es.sys_train(a.ncal, qcal.cpu().numpy())
     torch.cuda.synchronize()
-    return dict(ab=ab, W=W, dev=dev, base=base, qcal=qcal, qtest=qtest, ix=ix, gD=gD_h, es=es,
+    return dict(ab=ab, W=W, dev=dev, base=base, qcal=qcal, qtest=qtest, ix=ix, gD=gD_h, es=es, shape=shape,
                 setup_s=time.time() - t0)
 
 
+# ----------------------------------------------------------------------------- small-batch regime
+def hbm_bound_section(a, S, peaks, batches=(1, 64), calls=48):
+    """Batch 1 (the reference's latency mode, eval/bound.cpp:390-396) and batch 64: every query streams
+    its own lists, so algorithmic bytes = ndis * 4d are (nearly) the unique bytes and the HBM roofline
+    applies.  Two fractions: bytes / scan-kernel time, and bytes / whole call (what a user sees)."""
+    import torch
+    ix, W, dev = S["ix"], S["W"], S["dev"]
+    d = W.SHAPES[S["shape"]]["d"]
+    out = {}
+    for b in batches:
+        ncalls = max(4, min(calls, a.nq // b))
+        acc = torch.full((b,), 1.0 - a.eb, device=dev)
+        npb = torch.zeros(b, device=dev, dtype=torch.int64)
+        D = torch.empty(b, MAX_TOPK, device=dev)
+        I = torch.empty(b, MAX_TOPK, device=dev, dtype=torch.int64)
+        ix.set_params(*HYPER[a.eb])
+        ms, scan, ndis, wall = [], [], [], []
+        for c in range(ncalls + 3):
+            q = S["qtest"][(c * b) % (a.nq - b + 1):][:b]
+            npb.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ix.search_bounded_device(q, MAX_TOPK, QUERY_TOPK, acc, npb, D, I)
+            w = time.perf_counter() - t0
+            if c >= 3:
+                st = ix.stats()
+                ms.append(st["search_ms"])
+                scan.append(st["scan_ms"])
+                ndis.append(st["ndis"])
+                wall.append(w * 1e3)
+        bytes_call = float(np.mean(ndis)) * 4 * d
+        out[str(b)] = {
+            "calls": ncalls, "ms_per_call_device": float(np.mean(ms)), "ms_per_call_wall": float(np.mean(wall)),
+            "scan_ms": float(np.mean(scan)), "qps": b / (float(np.mean(wall)) / 1e3),
+            "alg_bytes_per_call": bytes_call,
+            "scan_gbs": bytes_call / (float(np.mean(scan)) / 1e3) / 1e9,
+            "scan_frac_of_hbm_peak": bytes_call / (float(np.mean(scan)) / 1e3) / 1e9 / peaks["hbm"],
+            "call_gbs": bytes_call / (float(np.mean(ms)) / 1e3) / 1e9,
+            "call_frac_of_hbm_peak": bytes_call / (float(np.mean(ms)) / 1e3) / 1e9 / peaks["hbm"]}
+    return out
+
+
+# ----------------------------------------------------------------------------- shards (config 3)
+def shards_section(a, world, rank, local, steps, warmup):
+    """BASELINE config 3: 10M x 96 DEEP-shaped inner product, k = 100, fixed nprobe; the database is
+    split over the ranks (id % world, copy_subset_to type 1), queries go to every rank, one
+    ncclAllGather + merge inside the library.  Strong scaling (total work fixed)."""
+    import torch
+    import torch.distributed as dist
+
+    import auncel_b200 as ab
+    from auncel_b200 import distributed as AD
+    from auncel_b200 import workload as W
+    dev = torch.device(f"cuda:{local}")
+    shape, K, nprobe = "deep", 100, a.shards_nprobe
+    d, metric = W.SHAPES[shape]["d"], W.SHAPES[shape]["metric"]
+    t0 = time.time()
+    base = W.make_vectors(shape, a.nb, 321, dev)       # every rank draws the same base ...
+    q = W.make_vectors(shape, a.nq, 654, dev)           # ... and the same queries
+    # shared quantizer: trained identically on every rank (same data, same seed, deterministic k-means)
+    sh = ab.IndexIVFFlat(d, a.nlist, metric, device=local)
+    gp = torch.Generator(device=dev)
+    gp.manual_seed(5)
+    sel = torch.randperm(a.nb, generator=gp, device=dev)[:min(a.nb, 64 * a.nlist)]
+    sh.train(base[sel].cpu().numpy(), niter=6)
+    cent = sh.centroids()
+    ids = torch.arange(rank, a.nb, world, device=dev)
+    sh.add_device(base[ids].contiguous(), ids.cpu().numpy())
+    sh.nprobe = nprobe
+    g = AD.NcclShardGroup(sh)
+    D = torch.empty(a.nq, K, device=dev)
+    I = torch.empty(a.nq, K, device=dev, dtype=torch.int64)
+    setup_s = time.time() - t0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        g.search_device(q, K, D, I)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lms, ams, mms = [], [], []
+    t_wall = time.perf_counter()
+    for _ in range(steps):
+        g.search_device(q, K, D, I)
+        st = g.stats()
+        lms.append(st["local_ms"])
+        ams.append(st["allgather_ms"])
+        mms.append(st["merge_ms"])
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3 / steps
+    step_ms = float(np.mean(lms)) + float(np.mean(ams)) + float(np.mean(mms))  # device time on the index stream
+    t = torch.tensor([step_ms, wall_ms, float(np.mean(lms)), float(np.mean(ams)), float(np.mean(mms))], device=dev,
+                     dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, wall_ms, l_ms, a_ms, m_ms = [float(v) for v in t]
+    out = {"workload": f"IVF-Flat nlist={a.nlist}, {a.nb}x{d} deep-shaped inner product, {a.nq} queries, k={K}, "
+                       f"nprobe={nprobe}, lists split id % {world}",
+           "parallelism": f"shards x{world}: 1 ncclAllGather of the packed (D|I) tables + merge per step",
+           "scaling": "strong", "value": a.nq / (step_ms / 1e3), "unit": "queries/s", "ms_per_step": step_ms,
+           "ms_per_step_wall": wall_ms, "local_search_ms": l_ms, "allgather_ms": a_ms, "merge_ms": m_ms,
+           "allgather_bytes_per_step_per_rank": st["allgather_bytes"], "nccl_version": st["nccl_version"],
+           "collective_share_of_step": (a_ms + m_ms) / step_ms, "setup_s": setup_s}
+    # parity: the merged result equals the unsharded index (tests/test_merge.cpp:94-152 invariant)
+    if world > 1:
+        nchk = 512
+        if rank == 0:
+            one = ab.IndexIVFFlat(d, a.nlist, metric, device=local)
+            one.set_centroids(cent, compute_interdis=False)
+            one.add_device(base)
+            one.nprobe = nprobe
+            D1 = torch.empty(nchk, K, device=dev)
+            I1 = torch.empty(nchk, K, device=dev, dtype=torch.int64)
+            one.search_device(q[:nchk], K, D1, I1)
+            out["parity_vs_single_index"] = {
+                "queries": nchk, "distances_bit_equal": bool(torch.equal(D1, D[:nchk])),
+                "labels_equal_frac": float((I1 == I[:nchk]).float().mean())}
+            del one
+        dist.barrier()
+    del g, sh, base
+    torch.cuda.empty_cache()
+    return out
+
+
+# ----------------------------------------------------------------------------- main arm
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -187,6 +336,10 @@ def run_ours(a):
         wall = time.perf_counter() - t0
         return ix.stats(), wall
 
+    import ctypes as C
+    L.auncel_index_search_bounded.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+
     def step_host(eb):
         hacc.fill_(1.0 - eb)
         hnp.zero_()
@@ -195,10 +348,6 @@ def run_ours(a):
         _ck(L.auncel_index_search_bounded(ix.h, n, hx.data_ptr(), MAX_TOPK, QUERY_TOPK, hacc.data_ptr(), None,
                                           hnp.data_ptr(), None, 0, hD.data_ptr(), hI.data_ptr()))
         return time.perf_counter() - t0
-
-    import ctypes as C
-    L.auncel_index_search_bounded.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
-                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
 
     def barrier():
         torch.cuda.synchronize()
@@ -216,8 +365,9 @@ def run_ours(a):
     sampler.start()
     barrier()
     dev_ms, scan_ms, ndis, launches, scan_launches = [], [], [], 0, 0
-    tcs = {k: [] for k in ("tc_ms", "tc_ndis", "simt_ms", "simt_ndis", "tc_rounds", "tc_uniq", "tc_staged", "simt_uniq",
-                           "simt_staged")}
+    keys = ("tc_ms", "tc_ndis", "simt_ms", "simt_ndis", "tc_rounds", "tc_uniq", "tc_staged", "simt_uniq", "simt_staged",
+            "rounds", "coarse_ms")
+    tcs = {k: [] for k in keys}
     t_region = time.perf_counter()
     for _ in range(a.steps):
         st, _ = step_device(a.eb)
@@ -241,22 +391,24 @@ def run_ours(a):
     ms_step = float(np.mean(dev_ms))
     e2e_step = float(np.mean(e2e_s))
     per_rank_ms = [ms_step]
-    if world > 1:
-        mine = torch.tensor([ms_step], device=dev, dtype=torch.float64)
-        allr = torch.empty(world, device=dev, dtype=torch.float64)
-        dist.all_gather_into_tensor(allr, mine)
-        per_rank_ms = [float(v) for v in allr.cpu()]
-        t = torch.tensor([ms_step, e2e_step], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, e2e_step = float(t[0]), float(t[1])
-    total_q = n * world
-
     # ---- quality on this rank's queries
     rec = W.recall_at(gt_test, D_eb, QUERY_TOPK, metric)
     quality = {"mean_recall@10": float(rec.mean()), "min_recall@10": float(rec.min()),
                "satisfied_frac": float((rec >= 1.0 - a.eb - 1e-6).mean()),
                "mean_my_nprobe": float(np_eb.mean()), "max_my_nprobe": int(np_eb.max())}
-    other = {}
+    if world > 1:
+        mine = torch.tensor([ms_step, quality["satisfied_frac"], quality["mean_recall@10"]], device=dev, dtype=torch.float64)
+        allr = torch.empty(world, 3, device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(allr, mine[None])
+        per_rank_ms = [float(v) for v in allr[:, 0].cpu()]
+        quality["satisfied_frac_min_over_ranks"] = float(allr[:, 1].min())
+        quality["mean_recall@10_min_over_ranks"] = float(allr[:, 2].min())
+        t = torch.tensor([ms_step, e2e_step], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_step = float(t[0]), float(t[1])
+    total_q = n * world
+
+    other, curve = {}, {}
     if rank == 0:
         for eb in (0.05, 0.2):
             if abs(eb - a.eb) < 1e-9:
@@ -266,56 +418,69 @@ def run_ours(a):
             other[str(eb)] = {"qps": n / (st["search_ms"] / 1e3), "mean_recall@10": float(r.mean()),
                               "satisfied_frac": float((r >= 1.0 - eb - 1e-6).mean()),
                               "mean_my_nprobe": float(np_t.cpu().numpy().mean())}
+        # how hard the synthetic workload is: fixed-nprobe recall@10 (cf. benchs/README.md:229-241 of the reference)
+        m = min(n, 2000)
+        for npb in (1, 4, 16, 64, 256):
+            ix.nprobe = npb
+            ix.search_device(S["qtest"][:m], MAX_TOPK, D_t[:m], I_t[:m])
+            curve[str(npb)] = float(W.recall_at(gt_test[:m], D_t[:m].cpu().numpy(), QUERY_TOPK, metric).mean())
 
-    # ---- roofline of the dominant kernel.  Unit of work = one (query, vector) distance evaluation,
-    # 4d algorithmic bytes / 2d (IP) or 3d (L2) flops each.  The bulk of the work runs
-    # in tc_filter_kernel (TF32 tcgen05 filter; survivors recomputed exactly), the rest in the
-    # exact FP32 scan_kernel.  Both are timed inside the library with CUDA events on its stream.
-    peak, peak_src = load_peaks()
+    # ---- roofline of the dominant kernel, per launch.  Unit of work = one (query, vector) distance
+    # evaluation: 4d algorithmic bytes, 2d TF32 flops in tc_filter_kernel (survivors recomputed exactly).
+    # A list-batched kernel stages a list tile once for up to 256 queries, so the HBM-level figure is the
+    # UNIQUE bytes of the lists a launch touches (counted by the plan kernel), SURVEY 8d "B_uniq".
+    peaks = load_peaks()
     tc_ms, tc_ndis = float(np.mean(tcs["tc_ms"])), float(np.mean(tcs["tc_ndis"]))
     simt_ms, simt_ndis = float(np.mean(tcs["simt_ms"])), float(np.mean(tcs["simt_ndis"]))
-    tc_launches = float(np.mean(tcs["tc_rounds"]))
+    tc_launches = max(float(np.mean(tcs["tc_rounds"])), 1.0)
+    uniq_bytes = float(np.mean(tcs["tc_uniq"])) * 4 * d
+    staged_bytes = float(np.mean(tcs["tc_staged"])) * 4 * d
+    flops = tc_ndis * 2 * d
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * sm_mhz * 1e6 / 1e12  # FP32 lane-ops/s at the measured clock (no FMA on the exact path)
     flop_per_dis = 3 * d if metric == 1 else 2 * d
-    # DRAM bytes per tensor-core launch: measured with ncu on this very command (dram__bytes_read+write of
-    # the four tc_filter launches of a step, profiles/r01_scan_tc_ncu_v3.txt / r01_tc_traffic.txt)
-    tf32_peak = None
-    try:
-        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        tf32_peak = mp.get("bf16_tflops", 0) / 2.0 or None  # tf32 runs at half the measured dense bf16 rate
-    except Exception:
-        pass
-    tc_tflops = tc_ndis * 2 * d / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else None
+    hbm_gbs = uniq_bytes / (tc_ms / 1e3) / 1e9 if tc_ms > 0 else None
+    tf32_tflops = flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else None
+    hbm_frac = hbm_gbs / peaks["hbm"] if hbm_gbs else None
+    tensor_frac = tf32_tflops / peaks["tf32"] if (tf32_tflops and peaks["tf32"]) else None
+    intensity = flops / uniq_bytes if uniq_bytes else None
+    ridge = peaks["tf32"] * 1e12 / (peaks["hbm"] * 1e9) if peaks["tf32"] else None
+    bound = "hbm" if (intensity is None or ridge is None or intensity < ridge) else "tensor"
+    traffic = None
+    if os.path.exists(TC_TRAFFIC_FILE) and a.nb == 10_000_000 and d == 128 and a.nlist == 4096:
+        try:
+            traffic = json.load(open(TC_TRAFFIC_FILE)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    arena_bytes = a.nb * d * 4
+    all_flops = float(np.mean(ndis)) * 2 * d
+    floor_ms = max(arena_bytes / (peaks["hbm"] * 1e9), all_flops / (peaks["tf32"] * 1e12) if peaks["tf32"] else 0.0) * 1e3
     roofline = {
-        "kernel": "tc_filter_kernel", "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
-        "achieved": tc_ndis * 4 * d / (tc_ms / 1e3) / 1e9 if tc_ms > 0 else None,
-        "frac": tc_ndis * 4 * d / (tc_ms / 1e3) / 1e9 / peak if tc_ms > 0 else None,
-        "traffic": TC_TRAFFIC_PER_LAUNCH if (a.nb == 10_000_000 and d == 128 and a.nlist == 4096) else None,
-        "per_launch": {"alg_bytes": tc_ndis * 4 * d / max(tc_launches, 1), "ms": tc_ms / max(tc_launches, 1),
-                       "launches_per_step": tc_launches},
-        "dram": {"note": "compulsory traffic = bytes of the distinct lists each launch touches (counted by the plan "
-                         "kernel); staged = bytes TMA moved into shared memory (one list pass per 256-query tile). "
-                         "ncu per launch (profiles/r01_scan_tc_ncu_v3.txt): launches with ~1 query tile per list run "
-                         "at 6.76 TB/s DRAM (103 % of the measured copy peak); launches with 3-4 query tiles per "
-                         "list are bound by the tf32 MMA rate (tensor pipe 60 % active, 3.7 TB/s DRAM, 1.9x the "
-                         "arena because L2 keeps only part of a list between its query tiles)",
-                 "compulsory_bytes_per_step": float(np.mean(tcs["tc_uniq"])) * 4 * d,
-                 "staged_bytes_per_step": float(np.mean(tcs["tc_staged"])) * 4 * d,
-                 "compulsory_gbs": float(np.mean(tcs["tc_uniq"])) * 4 * d / (tc_ms / 1e3) / 1e9 if tc_ms > 0 else None,
-                 "staged_gbs": float(np.mean(tcs["tc_staged"])) * 4 * d / (tc_ms / 1e3) / 1e9 if tc_ms > 0 else None,
-                 "compulsory_frac_of_peak": float(np.mean(tcs["tc_uniq"])) * 4 * d / (tc_ms / 1e3) / 1e9 / peak if tc_ms > 0 else None},
-        "tensor": {"achieved_tflops_tf32": tc_tflops, "peak_tflops_tf32": tf32_peak,
-                   "frac": tc_tflops / tf32_peak if (tc_tflops and tf32_peak) else None,
-                   "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2"},
-        "note": "algorithmic bytes = ndis*4d as the reference streams them (one list pass per probing query); one "
-                "staged tile serves up to 256 queries, so achieved/peak > 1 is reuse -- the HBM-level figure is "
-                "`dram` (each launch reads the arena about once)",
+        "kernel": "tc_filter_kernel", "bound": bound, "peak_source": peaks["source"],
+        "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+        "achieved": hbm_gbs if bound == "hbm" else tf32_tflops,
+        "peak": peaks["hbm"] if bound == "hbm" else peaks["tf32"],
+        "frac": hbm_frac if bound == "hbm" else tensor_frac,
+        "traffic": traffic,
+        "per_launch": {"unique_bytes": uniq_bytes / tc_launches, "staged_bytes": staged_bytes / tc_launches,
+                       "tf32_flops": flops / tc_launches, "ms": tc_ms / tc_launches, "launches_per_step": tc_launches},
+        "arithmetic_intensity_flop_per_byte": intensity, "ridge_flop_per_byte": ridge,
+        "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": peaks["hbm"], "frac": hbm_frac,
+                "staged_gbs": staged_bytes / (tc_ms / 1e3) / 1e9 if tc_ms > 0 else None},
+        "tensor": {"achieved_tflops_tf32": tf32_tflops, "peak_tflops_tf32": peaks["tf32"], "frac": tensor_frac},
+        "reuse": {"note": "algorithmic bytes (ndis*4d, one list pass per probing query, as the reference streams "
+                          "them) over kernel time; NOT a bandwidth: one staged tile serves up to 256 queries",
+                  "algorithmic_gbs": tc_ndis * 4 * d / (tc_ms / 1e3) / 1e9 if tc_ms > 0 else None,
+                  "queries_per_staged_byte": tc_ndis * 4 * d / staged_bytes if staged_bytes else None},
         "exact_scan": {"kernel": "scan_kernel", "ms_per_step": simt_ms, "ndis": simt_ndis,
-                       "achieved_gbs": simt_ndis * 4 * d / (simt_ms / 1e3) / 1e9 if simt_ms > 0 else None,
-                       "compulsory_gbs": float(np.mean(tcs["simt_uniq"])) * 4 * d / (simt_ms / 1e3) / 1e9 if simt_ms > 0 else None,
+                       "unique_gbs": float(np.mean(tcs["simt_uniq"])) * 4 * d / (simt_ms / 1e3) / 1e9 if simt_ms > 0 else None,
                        "fp32_pipe_frac": simt_ndis * flop_per_dis / (simt_ms / 1e3) / 1e12 / fp32_peak if simt_ms > 0 else None},
-        "scan_share_of_step": float(np.mean(scan_ms)) / ms_step,
+        "step": {"ms_per_step": ms_step, "floor_ms": floor_ms, "frac_of_floor": floor_ms / ms_step,
+                 "note": "floor = max(one pass over the list arena at the HBM peak, all distance evaluations of the "
+                         "step as TF32 flops at the tensor peak)",
+                 "tc_filter_share": tc_ms / ms_step, "exact_scan_share": simt_ms / ms_step,
+                 "coarse_share": float(np.mean(tcs["coarse_ms"])) / ms_step,
+                 "rounds": float(np.mean(tcs["rounds"]))},
     }
 
     line = {
@@ -330,11 +495,29 @@ def run_ours(a):
         "e2e": {"value": total_q / e2e_step, "unit": "queries/s", "h2d_bytes_per_step": n * d * 4 + n * 4 + n * 8,
                 "d2h_bytes_per_step": n * MAX_TOPK * 12 + n * 8, "ms_per_step": 1e3 * e2e_step},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "quality": quality,
-        "error_bounds": other, "setup_s": S["setup_s"], "timed_region_s": region_s,
+        "error_bounds": other, "fixed_nprobe_recall@10": curve, "setup_s": S["setup_s"], "timed_region_s": region_s,
         "per_rank_ms_per_step": per_rank_ms,
     }
     if rank == 0 and world == 1 and not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline(a, S, np_eb, D_eb)
+    if not a.no_extras:
+        if rank == 0:
+            hb = {"sift": hbm_bound_section(a, S, peaks)}
+        # free the headline index before the other shapes are built
+        del ix
+        S.clear()
+        torch.cuda.empty_cache()
+        if rank == 0 and world == 1 and a.shape == "sift":
+            St = build_everything(a, local, rank, shape="text")
+            hb["text"] = hbm_bound_section(a, St, peaks)
+            hb["text"]["setup_s"] = St["setup_s"]
+            St.clear()
+            torch.cuda.empty_cache()
+        if rank == 0:
+            line["hbm_bound"] = hb
+        sh = shards_section(a, world, rank, local, max(3, a.steps), max(3, a.warmup))
+        if rank == 0:
+            line["shards"] = sh
     if rank == 0:
         emit(line)
     if world > 1:
@@ -342,6 +525,7 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- reference arm
 def build_reference(a, S):
     """The unmodified reference with the same index content: same centroids, the same list
     assignment (precomputed_idx, IndexIVFFlat.cpp:41-59), same ground truth, same traces."""
@@ -359,6 +543,11 @@ def build_reference(a, S):
     return R, O
 
 
+SETUP_NOTE = ("setup (synthetic data, k-means, list assignment, ground truth, calibration traces) ran through "
+              "auncel_b200 on the GPU and was handed to the reference (centroids, precomputed list numbers, traces); "
+              "the timed region is the unmodified reference alone")
+
+
 def cpu_sample_search(a, S, R, O, nsample, threads):
     """Error_sys::search of the reference over `nsample` test queries on `threads` host threads."""
     ix = S["ix"]
@@ -373,9 +562,14 @@ def cpu_sample_search(a, S, R, O, nsample, threads):
     acc = np.full(ncal + nsample, 1.0 - a.eb, np.float32)
     R.set_queries(QUERY_TOPK, nsample, q, acc, *HYPER[a.eb])
     t0 = time.perf_counter()
-    D, I = R.es_search(ncal, nsample, threads=threads)
+    D, I = R.es_search(ncal, nsample, threads=threads, chunk=4)  # dynamic hand-out, 4 queries at a time
     dt = time.perf_counter() - t0
     return dt, D, R.my_nprobe(ncal, nsample)
+
+
+def cpu_sample_size(a, cores):
+    nround = max(10, (a.nq // 10) * 10)
+    return a.cpu_sample or min(nround, max(1000, (32 * cores) // 10 * 10))
 
 
 def cpu_baseline(a, S, np_gpu, D_gpu):
@@ -384,14 +578,14 @@ def cpu_baseline(a, S, np_gpu, D_gpu):
         return {"value": None, "unit": "queries/s", "cores": 0, "kind": "reference",
                 "sample": "oracle/_ref/libauncel_ref.so missing"}
     cores = os.cpu_count() or 1
-    nround = max(10, (a.nq // 10) * 10)
-    nsample = a.cpu_sample or min(nround, max(200, (8 * cores) // 10 * 10))
+    nsample = cpu_sample_size(a, cores)
     R, O = build_reference(a, S)
     dt, D, mynp = cpu_sample_search(a, S, R, O, nsample, cores)
     R.close()
     return {"value": nsample / dt, "unit": "queries/s", "cores": cores, "kind": "reference",
-            "sample": f"first {nsample} test queries, one batched Error_sys::search on {cores} host threads "
-                      f"(unmodified reference, exact-difference coarse path, OpenBLAS unused), {dt:.2f} s",
+            "sample": f"first {nsample} test queries, one batched Error_sys::search on {cores} host threads drawing 4 "
+                      f"queries at a time (unmodified reference, exact-difference coarse path, OpenBLAS unused), {dt:.2f} s",
+            "setup": SETUP_NOTE,
             "parity_on_sample": {"my_nprobe_equal": bool(np.array_equal(mynp.astype(np.int64), np_gpu[:nsample])),
                                  "distances_bit_equal": bool(np.array_equal(D, D_gpu[:nsample])),
                                  "my_nprobe_mismatches": [[int(i), int(mynp[i]), int(np_gpu[i])] for i in
@@ -412,7 +606,7 @@ def run_reference(a):
     W = S["W"]
     d = W.SHAPES[a.shape]["d"]
     cores = os.cpu_count() or 1
-    nsample = a.cpu_sample or min(max(10, a.nq // 10 * 10), max(200, (8 * cores) // 10 * 10))
+    nsample = cpu_sample_size(a, cores)
     R, O = build_reference(a, S)
     times = []
     for i in range(a.warmup + a.steps):
@@ -431,7 +625,8 @@ def run_reference(a):
                                f"max_topk={MAX_TOPK}, query_topk={QUERY_TOPK}, error bound {a.eb}, "
                                f"(multipler,std_m)={HYPER[a.eb]}"},
         "cpu_baseline": {"value": v, "unit": "queries/s", "cores": cores, "kind": "reference",
-                         "sample": f"{nsample} test queries per step, batched Error_sys::search on {cores} threads"},
+                         "sample": f"{nsample} test queries per step, batched Error_sys::search on {cores} threads "
+                                   f"drawing 4 queries at a time", "setup": SETUP_NOTE},
         "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0})
 

@@ -145,6 +145,7 @@ def ref():
                                            C.c_long, C.c_float, C.c_float, C.c_int, C.c_int]
         lib.ref_es_search.argtypes = [C.c_void_p, _f, _l, C.c_long, C.c_long]
         lib.ref_es_search_threads.argtypes = [C.c_void_p, _f, _l, C.c_long, C.c_long, C.c_int]
+        lib.ref_es_search_threads_chunk.argtypes = [C.c_void_p, _f, _l, C.c_long, C.c_long, C.c_int, C.c_long]
         lib.ref_search_fixed_threads.argtypes = [C.c_void_p, C.c_long, _f, C.c_long, C.c_long, _f, _l, C.c_int]
         lib.ref_get_my_nprobe.argtypes = [C.c_void_p, C.c_long, C.c_long, _ul]
         lib.ref_clear_my_nprobe.argtypes = [C.c_void_p]
@@ -311,7 +312,7 @@ class RefIndex:
                                         len(acc), multipler, std_m, int(profile),
                                         int(overhead_profile)))
 
-    def es_search(self, start, num, search_size=-1, threads=0, virtual_clock=False):
+    def es_search(self, start, num, search_size=-1, threads=0, virtual_clock=False, chunk=0):
         """search_size=-1: one batched call over `num` queries; 1: the eval/bound.cpp loop."""
         if virtual_clock:  # error_pro::time_tune left set by time_search: the cut needs the test clock
             self.lib.ref_set_virtual_clock(1)
@@ -323,7 +324,7 @@ class RefIndex:
         D = np.empty((num, k), np.float32)
         I = np.empty((num, k), np.int64)
         if threads > 1:
-            _ck(self.lib.ref_es_search_threads(self.h, _p(D, _f), _p(I, _l), start, num, threads))
+            _ck(self.lib.ref_es_search_threads_chunk(self.h, _p(D, _f), _p(I, _l), start, num, threads, chunk))
         elif search_size == -1:
             _ck(self.lib.ref_es_search(self.h, _p(D, _f), _p(I, _l), start, -1))
         else:

@@ -18,6 +18,7 @@
 #include <sys/time.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -377,7 +378,15 @@ int ref_get_t_recalls(void* h, long start, long n, float* out) {
  * IndexIVF::search on a contiguous query slice (the same static split an `omp
  * for` would do); per-query state (my_nprobe[id], t_recalls[id]) is indexed by
  * global id so slices do not interfere. */
+int ref_es_search_threads_chunk(void* h, float* D, long* I, long start, long num, int nthreads, long chunk);
 int ref_es_search_threads(void* h, float* D, long* I, long start, long num, int nthreads) {
+    return ref_es_search_threads_chunk(h, D, I, start, num, nthreads, 0);
+}
+
+/* chunk == 0: static contiguous slices (what `omp for` does by default); chunk > 0: the threads draw
+ * `chunk` queries at a time from a shared counter (`schedule(dynamic, chunk)`), so one query with a
+ * very large my_nprobe does not set the time of the whole call. */
+int ref_es_search_threads_chunk(void* h, float* D, long* I, long start, long num, int nthreads, long chunk) {
     Ref* r = (Ref*)h;
     REF_TRY
     faiss::IndexIVF* ix = r->index;
@@ -386,17 +395,21 @@ int ref_es_search_threads(void* h, float* D, long* I, long start, long num, int 
     ix->nprobe = ix->nlist;
     std::vector<std::thread> th;
     std::vector<std::string> errs(nthreads);
-    long per = (num + nthreads - 1) / nthreads;
+    long per = chunk > 0 ? chunk : (num + nthreads - 1) / nthreads;
+    std::atomic<long> next(0);
     for (int t = 0; t < nthreads; t++) {
-        long q0 = t * per, q1 = std::min(num, q0 + per);
-        if (q0 >= q1) break;
-        th.emplace_back([=, &errs]() {
+        th.emplace_back([=, &errs, &next]() {
             omp_set_num_threads(1);
-            try {
-                ix->search(q1 - q0, r->queries.data() + (size_t)(start + q0) * r->d, k,
-                           D + q0 * k, I + q0 * k, (size_t)(start + q0));
-            } catch (const std::exception& e) {
-                errs[t] = e.what();
+            for (;;) {
+                long q0 = next.fetch_add(per), q1 = std::min(num, q0 + per);
+                if (q0 >= q1) break;
+                try {
+                    ix->search(q1 - q0, r->queries.data() + (size_t)(start + q0) * r->d, k,
+                               D + q0 * k, I + q0 * k, (size_t)(start + q0));
+                } catch (const std::exception& e) {
+                    errs[t] = e.what();
+                    break;
+                }
             }
         });
     }
