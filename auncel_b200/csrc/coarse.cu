@@ -400,11 +400,12 @@ template <int METRIC>
 __global__ void __launch_bounds__(32)
 heap_order_kernel(const float* __restrict__ raw, long nlist, int k, const int* __restrict__ entry,
                   const int* __restrict__ fix_list, const int* __restrict__ nfix, float* __restrict__ out_dis,
-                  int* __restrict__ out_keys, int* __restrict__ tie0) {
+                  int* __restrict__ out_keys, int* __restrict__ tie0, const int* __restrict__ qbound) {
     if ((int)blockIdx.x >= *nfix) return;
     extern __shared__ __align__(16) unsigned long long hp[];  // hp[0] unused: 1-based heap, 16 B aligned pairs
     unsigned long long* h = hp;
-    const long q = fix_list[blockIdx.x];
+    const long q = fix_list[blockIdx.x] & 0x3fffffff;
+    const bool straddle = (fix_list[blockIdx.x] >> 30) & 1;  // only the tie group around the query's stop stage
     const int lane = threadIdx.x;
     const float neut = METRIC == METRIC_L2 ? FLT_MAX : -FLT_MAX;
     uint32_t on = f2ord(neut);
@@ -585,7 +586,18 @@ heap_order_kernel(const float* __restrict__ raw, long nlist, int k, const int* _
     if (lane == 0 && blockIdx.x == 0)
         printf("heap_order: nfix %d k %d phase1 %lld cycles, phase2 %lld cycles\n", *nfix, k, t1 - t0, clock64() - t1);
 #endif
-    for (int i = lane; i < k; i += 32) {
+    int w_lo = 0, w_hi = k - 1;
+    if (straddle) {
+        // A decided query scans ranks [0, b): equal distances strictly inside that range cannot change what
+        // is scanned, only a tie between rank b-1 and rank b can.  Ranks below the group may already have
+        // been scanned in the provisional order (finalize maps rank -> list), so only the group is rewritten.
+        const int b = qbound[q];
+        const uint32_t o = node_ord(hp[b]);  // rank b-1 lives in hp[b]
+        w_lo = w_hi = b - 1;
+        while (w_lo > 0 && node_ord(hp[w_lo]) == o) w_lo--;
+        while (w_hi + 1 < k && node_ord(hp[w_hi + 2]) == o) w_hi++;
+    }
+    for (int i = w_lo + lane; i <= w_hi; i += 32) {
         const unsigned long long node = hp[i + 1];
         uint32_t o = (uint32_t)(node >> 32);
         if (METRIC == METRIC_IP) o = ~o;
@@ -640,26 +652,41 @@ void heap_entry_table(int k, std::vector<int>& entry) {
 
 // queries (from `list`, or all n when list == nullptr) whose first tie lies below `bound`
 __global__ void collect_ties_kernel(const int* __restrict__ list, int n, const int* __restrict__ tie0, int bound,
-                                    const int* __restrict__ qbound, int* __restrict__ fix_list,
-                                    int* __restrict__ nfix) {
+                                    const int* __restrict__ qbound, const int* __restrict__ decided, int r0, int k,
+                                    long nlist, const float* __restrict__ dis, int* __restrict__ fix_list,
+                                    int* __restrict__ nfix, int* __restrict__ err) {
     int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
     int q = list ? list[a] : a;
+    if (decided && decided[q]) {
+        // stop stage b known: the order inside [0, b) is irrelevant (every list in it is scanned, the check
+        // no longer runs); what must follow the reference's heap is WHICH lists are in it, i.e. a tie
+        // between rank b-1 and rank b -- looked at in the round that scans rank b-1
+        const int b = qbound[q];
+        if (tie0[q] != 0x7fffffff && b > r0 && b <= bound && b < k &&
+            dis[(long)q * nlist + b - 1] == dis[(long)q * nlist + b]) {
+            // the run of equal distances reaches back into ranks that were scanned in the provisional order
+            if (err && r0 > 0 && dis[(long)q * nlist + r0 - 1] == dis[(long)q * nlist + b]) atomicOr(err, ERR_TIE_SPAN);
+            fix_list[atomicAdd(nfix, 1)] = q | (1 << 30);
+        }
+        return;
+    }
     int b = qbound ? min(bound, qbound[q]) : bound;  // a decided query never scans past its stop stage
     if (tie0[q] < b) fix_list[atomicAdd(nfix, 1)] = q;
 }
 
 void launch_fix_ties(int metric, const float* raw, long nlist, int k, const int* entry, const int* list, int n,
                      int* tie0, int bound, const int* qbound, int* fix_list, int* nfix, float* out_dis, int* out_keys,
-                     cudaStream_t s) {
+                     cudaStream_t s, const int* decided, int r0, int* err) {
     if (n == 0) return;
     CUDA_CHECK(cudaMemsetAsync(nfix, 0, sizeof(int), s));
-    collect_ties_kernel<<<(n + 255) / 256, 256, 0, s>>>(list, n, tie0, bound, qbound, fix_list, nfix);
+    collect_ties_kernel<<<(n + 255) / 256, 256, 0, s>>>(list, n, tie0, bound, qbound, decided, r0, k, nlist, out_dis,
+                                                        fix_list, nfix, err);
     size_t smem = (size_t)(k + 2) * 8;
     AUNCEL_CHECK(smem <= 220 * 1024, "nlist too large for the exact tie replay");
     auto kern = metric == METRIC_L2 ? heap_order_kernel<METRIC_L2> : heap_order_kernel<METRIC_IP>;
     if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<n, 32, smem, s>>>(raw, nlist, k, entry, fix_list, nfix, out_dis, out_keys, tie0);
+    kern<<<n, 32, smem, s>>>(raw, nlist, k, entry, fix_list, nfix, out_dis, out_keys, tie0, qbound);
     CUDA_CHECK(cudaGetLastError());
 }
 

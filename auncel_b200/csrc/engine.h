@@ -153,6 +153,8 @@ struct IvfIndex {
     DevBuf<float> vnorm, qnorm;              // squared norms of arena rows / of the batch's queries
     DevBuf<unsigned long long> tc_cand;      // survivors of the tensor-core filter
     DevBuf<int> pair_flag;                   // per slot: overflowed in a tensor-core round
+    DevBuf<unsigned char> redo_pool;         // exact redo of those pairs: compact pool, 4 sub-slots per pair
+    DevBuf<int> redo_cnt, redo_ord;
     int tc_mode = 1;                         // 0 off, 1 automatic, 2 whenever every active heap is full
     int tc_audit = 0;                        // tests: redo every tensor-core round exactly and compare the slots
     DevBuf<unsigned char> audit_pool;
@@ -174,7 +176,7 @@ struct IvfIndex {
     // probe iteration / of one scanned code.  Default: a B200 streaming a list at HBM speed.
     long long time_us_per_list = 2, time_ns_per_code = 0;
 
-    size_t pool_budget_bytes = (size_t)4 << 30;
+    size_t pool_budget_bytes = (size_t)16 << 30;  // candidate pools are sparse; 180 GB of HBM make a wide window cheap
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     cudaEvent_t ev_in = nullptr;  // auncel_index_wait_stream: orders this stream behind a caller stream
@@ -226,7 +228,8 @@ void launch_rank_rows(int metric, const float* dis, long nq, long nlist, float* 
 // coarse distances below rank `bound`; rewrites their rows of out_dis/out_keys in heap order
 void heap_entry_table(int k, std::vector<int>& entry);
 void launch_fix_ties(int metric, const float* raw, long nlist, int k, const int* entry, const int* list, int n,
-                     int* tie0, int bound, const int* qbound, int* fix_list, int* nfix, float* out_dis, int* out_keys, cudaStream_t s);
+                     int* tie0, int bound, const int* qbound, int* fix_list, int* nfix, float* out_dis, int* out_keys, cudaStream_t s,
+                     const int* decided = nullptr, int r0 = 0, int* err = nullptr);
 void launch_interdis(int metric, const float* cent, long nlist, int dpad, float* out, cudaStream_t s);
 void launch_merge_tables(int metric, long n, long k, long nshard, const float* all_D,
                          const long long* all_I, const long long* translations, float* D,

@@ -44,6 +44,7 @@ enum : int {
     ERR_ARCOS_DOMAIN = 1,    // IVF_pro.cpp:180 throws outside [-1,1]
     ERR_ARCOS_EDGE = 2,      // x == 1 indexes arcos_list[500] of 500 (IVF_pro.cpp:182)
     ERR_COSINE_PRECOND = 4,  // IVF_pro.cpp:42 throws when a > b
+    ERR_TIE_SPAN = 8,        // (engine) a run of equal centroid distances spans a round boundary and the stop stage
 };
 
 // error_pro::arcos, IVF_pro.cpp:179-184:  int index = x*arcos_size/2 + arcos_size/2;

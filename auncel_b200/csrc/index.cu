@@ -453,7 +453,8 @@ void IvfIndex::search(const QueryBatch& qb) {
     int n_active = h_list_off[nlist] > 0 ? (int)n : 0;  // an empty index has nothing to scan
     int min_rcnt = 0, not_full = (int)n;
     bool ties_done = false;
-    const int tc_min_r0 = getenv("AUNCEL_TC_MIN_R0") ? atoi(getenv("AUNCEL_TC_MIN_R0")) : 2;
+    const int tc_min_r0 = getenv("AUNCEL_TC_MIN_R0") ? atoi(getenv("AUNCEL_TC_MIN_R0")) : 1;
+    const int wide_slot_r0 = getenv("AUNCEL_WIDE_R0") ? atoi(getenv("AUNCEL_WIDE_R0")) : 8;  // rounds starting below this rank get wide slots
     int r0 = 0;
     int* act_cur = active.p;
     int* act_nxt = active2.p;
@@ -465,7 +466,7 @@ void IvfIndex::search(const QueryBatch& qb) {
         // its window with the rank already reached (see below), so undecided queries never speculate
         // past what the reference itself would scan.
         long w_cap = (long)(pool_budget_bytes / ((size_t)n_active * ((size_t)K * 8 + (size_t)dpad * 4)));
-        static const long w_hard = getenv("AUNCEL_WMAX") ? atol(getenv("AUNCEL_WMAX")) : 1024;
+        static const long w_hard = getenv("AUNCEL_WMAX") ? atol(getenv("AUNCEL_WMAX")) : 4096;
         w_cap = std::max(1L, std::min<long>(w_cap, w_hard));
         long w = max_stage - r0;
         if (qb.mode == 1 && !qb.overhead_profile) {
@@ -482,9 +483,13 @@ void IvfIndex::search(const QueryBatch& qb) {
             // the round after the first list still runs on the exact FP32 scan (loose thresholds would
             // overflow the tensor-core filter's per-pair slots): keep it short, the filter takes over next
             // (measured: 3 lists at d = 128, no cap at d = 96 where the exact scan is cheaper per pair)
+            // Large batches: the round after the first list already runs on the tensor-core filter (wide
+            // slots).  Such a round streams every list once whatever the number of pairs per list (up to a
+            // tile of queries), so it covers more ranks than the growth rule alone would give: ranks an
+            // early-deciding query does not need cost filter flops only, and one pass over the arena is saved.
             static const long w1_env = getenv("AUNCEL_W1") ? atol(getenv("AUNCEL_W1")) : -1;
-            const long w1_cap = w1_env >= 0 ? w1_env : (dpad >= 128 ? 3 : 0);
-            if (w1_cap > 0 && stats.rounds == 1 && n >= 2048) w = std::min<long>(w, w1_cap);
+            const long w1 = w1_env >= 0 ? w1_env : 31;
+            if (w1 > 0 && stats.rounds == 1 && n >= 2048 && tc_mode == 1) w = std::min<long>(max_stage - r0, std::max<long>(w, w1));
         } else if ((long)n_active * max_stage >= 4096 && max_stage > 8) {
             // plain / calibration search: a few narrow rounds first, so that the bulk of the
             // lists is scanned against a tight threshold (cheap selection)
@@ -508,9 +513,14 @@ void IvfIndex::search(const QueryBatch& qb) {
         rp.qt = SCAN_QT / nsub;
         rp.nsub = nsub;
         rp.unsorted = 0;
+        rp.merged = 0;
         rp.defer_sort = n_active >= 1024 ? 1 : 0;  // few queries: one merge warp per query would sort serially
         rp.filtered = 0;
         rp.pair_flag = nullptr;
+        rp.redo_ord = nullptr;
+        rp.redo_d = nullptr;
+        rp.redo_off = nullptr;
+        rp.redo_cnt = nullptr;
         // tensor-core filter round: (nearly) every remaining query already holds K results, so only
         // a handful of vectors per list can still enter -- filter with TF32 MMAs, rerank exactly.
         // The few queries whose heaps are not full yet let everything through and are redone by
@@ -532,9 +542,16 @@ void IvfIndex::search(const QueryBatch& qb) {
         rp.w = (int)w;
         rp.S = (int)S;
         size_t slots = (size_t)n_active * w * S * nsub;
-        pool.ensure(slots * K * 8);
+        // slot capacity: K everywhere, except in the first tensor-core round(s) whose threshold comes from
+        // a single list -- there a pair can have a few hundred survivors, which merge_check reduces to
+        // the K best (sort in shared memory, capacity 2 * KP) instead of an exact redo of the pair
+        int KP = 16;
+        while (KP < K) KP <<= 1;
+        const int cap = (use_tc && r0 < wide_slot_r0) ? std::max(K, 2 * KP) : K;
+        rp.cap = cap;
+        pool.ensure(slots * cap * 8);
         rp.cand_d = reinterpret_cast<float*>(pool.p);
-        rp.cand_off = reinterpret_cast<unsigned*>(pool.p + slots * K * 4);
+        rp.cand_off = reinterpret_cast<unsigned*>(pool.p + slots * cap * 4);
         rp.slot_cnt = slot_cnt.ensure(slots);
         rp.pairs = pairs.ensure((size_t)n_active * w);
         rp.xq_sorted = q_sorted.ensure(((size_t)n_active * w + 256) * dpad);
@@ -551,10 +568,11 @@ void IvfIndex::search(const QueryBatch& qb) {
         if (exact_ties && !ties_all_upfront && !ties_done) {
             // ranks [r0, r0+w) are about to be scanned: their order must be the reference's.  Once
             // the remaining queries fit one replay wave, fix all of their ranks and stop checking.
-            const bool all_now = n_active <= 1000;
+            // Error-bounded search: a query whose stop stage is known only needs the tie AT that stage.
+            const bool all_now = n_active <= 1000 && qb.mode != 1;
             launch_fix_ties(metric, c_raw.p, nlist, nprobe, entry_table(nprobe), act_cur, n_active, c_tie0.p,
                             all_now ? nprobe : r0 + (int)w, rp.st.bound, fix_list.p, ctl.p + CTL_NFIX, c_dis.p,
-                            c_keys.p, stream);
+                            c_keys.p, stream, qb.mode == 1 ? rp.st.decided : nullptr, r0, ctl.p + CTL_ERR);
             ties_done = all_now;
         }
         CUDA_CHECK(cudaMemsetAsync(rp.round_work, 0, 4 * sizeof(unsigned long long), stream));
@@ -570,7 +588,7 @@ void IvfIndex::search(const QueryBatch& qb) {
             ta.c1 = 2.f * (1.02f / 512.f + (float)dpad / 2097152.f);
             ta.c2 = 1.f / 1048576.f;
             ta.c3 = 1.f / 16384.f;
-            ta.cand_cap = (int)std::min<size_t>((size_t)16 << 20, std::max<size_t>((size_t)n_active * w * 32, 1 << 20));
+            ta.cand_cap = (int)std::min<size_t>((size_t)64 << 20, std::max<size_t>((size_t)n_active * w * 32, 1 << 20));
             ta.cand = tc_cand.ensure(ta.cand_cap);
             ta.N = Ntc;
             alignas(64) unsigned char bmap[128];
@@ -591,6 +609,7 @@ void IvfIndex::search(const QueryBatch& qb) {
             CUDA_CHECK(cudaEventRecord(tc_ev[2 * tc_idx + 1], stream));
             launch_rerank(rp, ta, num_sms, stream);
             CUDA_CHECK(cudaMemcpyAsync(h_ctl.p, ctl.p, CTL_SIZE * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            if (!tc_audit) launch_slot_sort(rp, num_sms, stream);  // (the audit compares the raw survivor sets)
             CUDA_CHECK(cudaStreamSynchronize(stream));
             launches += 2;
             stats.tc_candidates += (uint64_t)h_ctl.p[CTL_NCAND];
@@ -610,6 +629,7 @@ void IvfIndex::search(const QueryBatch& qb) {
                 if (tc_audit) {
                     // exact rescan of the whole round into a second pool, slot-by-slot comparison
                     RoundParams ra = rp;
+                    ra.cap = K;
                     ra.qt = SCAN_QT;
                     ra.unsorted = 0;
                     ra.defer_sort = 0;
@@ -627,17 +647,40 @@ void IvfIndex::search(const QueryBatch& qb) {
                 if (h_ctl.p[CTL_OVERFLOW] > 0) {
                     // some (query, list) pairs had more than K survivors (loose or missing tau):
                     // the exact scan redoes just those pairs and rewrites their slots
-                    stats.tc_fallbacks += 0;
-                    rp.qt = SCAN_QT;
-                    rp.filtered = 1;
-                    launch_plan(rp, stream);
-                    launch_scan(rp, codes_tmap, qmap, num_sms, stream);
-                    rp.filtered = 0;
+                    // h_ctl[CTL_OVERFLOW] counts overflowing survivors, an upper bound of the flagged pairs
+                    const size_t nredo = std::min<size_t>((size_t)h_ctl.p[CTL_OVERFLOW], (size_t)n_active * w);
+                    redo_pool.ensure(nredo * 4 * K * 8);
+                    RoundParams rr = rp;
+                    rr.filtered = 1;
+                    rr.qt = SCAN_QT / 4;  // narrow tiles: 8 queries, the 128 rows of a block split over 4 warps
+                    rr.nsub = 4;
+                    rr.S = 1;
+                    rr.cap = K;
+                    rr.defer_sort = 0;
+                    rr.cand_d = reinterpret_cast<float*>(redo_pool.p);
+                    rr.cand_off = reinterpret_cast<unsigned*>(redo_pool.p + nredo * 4 * K * 4);
+                    rr.slot_cnt = redo_cnt.ensure(nredo * 4);
+                    rr.redo_ord = redo_ord.ensure((size_t)n_active * w);
+                    CUDA_CHECK(cudaMemsetAsync(rr.slot_cnt, 0, nredo * 4 * sizeof(int), stream));
+                    launch_plan(rr, stream);
+                    launch_scan(rr, codes_tmap, qmap, num_sms, stream);
+                    rp.redo_ord = rr.redo_ord;
+                    rp.redo_d = rr.cand_d;
+                    rp.redo_off = rr.cand_off;
+                    rp.redo_cnt = rr.slot_cnt;
                     launches += 5;
                 }
             }
         }
-        if (!scanned) launch_scan(rp, codes_tmap, qmap, num_sms, stream);
+        if (!scanned) {
+            launch_scan(rp, codes_tmap, qmap, num_sms, stream);
+            // few queries: many partial results per pair (segments x row subsets) -- merge them in parallel
+            // before the per-query sequential pass
+            if (S * nsub > 1 && !rp.defer_sort && (long)n_active * w <= 16384) {
+                launch_stage_merge(rp, num_sms, stream);
+                rp.merged = 1;
+            }
+        }
         CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds + 1], stream));
         launch_merge_check(rp, tp, stream);
         launches += 7 + (exact_ties && !ties_all_upfront ? 2 : 0);  // [collect_ties, heap_order,] plan x3, gather, scan, merge_check, compact_active

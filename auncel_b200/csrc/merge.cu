@@ -124,6 +124,186 @@ void launch_set_online(int metric, long nlist, long n, const float* cdis, const 
     CUDA_CHECK(cudaGetLastError());
 }
 
+// --------------------------------------------------------------------------- slot ordering
+// rerank_kernel appends the survivors of a (query, list) pair in arrival order.  merge_check needs them
+// ordered by (distance, offset) and only the K best; doing that inside its per-query stage loop would
+// serialise up to w sorts behind one warp, so the slots are ordered here, one warp per slot, all in parallel.
+constexpr int SS_WARPS = 8;
+constexpr int SS_MAX = 512;  // widest slot (entries)
+
+__global__ void __launch_bounds__(SS_WARPS * 32) slot_sort_kernel(RoundParams rp, long nslots) {
+    __shared__ unsigned long long s_key[SS_WARPS][SS_MAX];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = rp.K, cap = rp.cap, metric = rp.metric;
+    unsigned long long* key = s_key[warp];
+    const long nwarps = (long)gridDim.x * SS_WARPS;
+    for (long base = ((long)blockIdx.x * SS_WARPS + warp) * 32; base < nslots; base += nwarps * 32) {
+        // 32 slot counts per coalesced load, then the slots that need work one after the other
+        const long mine = base + lane;
+        const int cnt_l = mine < nslots ? rp.slot_cnt[mine] : 0;
+        const bool todo_l = !(cnt_l & SLOT_SORTED) && (cnt_l & ~SLOT_SORTED) > 1 && (cnt_l & ~SLOT_SORTED) <= cap;
+        unsigned todo = __ballot_sync(0xffffffffu, todo_l);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const long slot = base + src;
+            const int rc = __shfl_sync(0xffffffffu, cnt_l, src);
+            float* cd = rp.cand_d + slot * cap;
+            unsigned* co = rp.cand_off + slot * cap;
+            if (rc <= 32) {
+                unsigned long long kk = ~0ull;
+                if (lane < rc) {
+                    uint32_t o = f2ord(cd[lane]);
+                    if (metric == METRIC_IP) o = ~o;
+                    kk = ((unsigned long long)o << 32) | co[lane];
+                }
+#pragma unroll
+                for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+                    for (int j = k2 >> 1; j > 0; j >>= 1) {
+                        const unsigned long long other = __shfl_xor_sync(0xffffffffu, kk, j);
+                        const bool up = ((lane & k2) == 0), lower = ((lane & j) == 0);
+                        const unsigned long long mn = kk < other ? kk : other, mx = kk < other ? other : kk;
+                        kk = (lower == up) ? mn : mx;
+                    }
+                if (lane < min(rc, K)) {
+                    uint32_t o = (uint32_t)(kk >> 32);
+                    if (metric == METRIC_IP) o = ~o;
+                    cd[lane] = ord2f(o);
+                    co[lane] = (unsigned)(kk & 0xffffffffu);
+                }
+            } else {
+                int P = 64;
+                while (P < rc) P <<= 1;
+                for (int i = lane; i < P; i += 32) {
+                    unsigned long long kk = ~0ull;
+                    if (i < rc) {
+                        uint32_t o = f2ord(cd[i]);
+                        if (metric == METRIC_IP) o = ~o;
+                        kk = ((unsigned long long)o << 32) | co[i];
+                    }
+                    key[i] = kk;
+                }
+                __syncwarp();
+                for (int size = 2; size <= P; size <<= 1)
+                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                        for (int t = lane; t < P / 2; t += 32) {
+                            const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                            const bool up = ((lo & size) == 0);
+                            const unsigned long long x = key[lo], y = key[hi];
+                            if ((x > y) == up) {
+                                key[lo] = y;
+                                key[hi] = x;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                for (int i = lane; i < min(rc, K); i += 32) {
+                    const unsigned long long kk = key[i];
+                    uint32_t o = (uint32_t)(kk >> 32);
+                    if (metric == METRIC_IP) o = ~o;
+                    cd[i] = ord2f(o);
+                    co[i] = (unsigned)(kk & 0xffffffffu);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) rp.slot_cnt[slot] = min(rc, K) | SLOT_SORTED;
+        }
+    }
+}
+
+// Exact rounds with few queries split every list into S segments x nsub row subsets so that all SMs have
+// work; each (query, rank) then owns S * nsub partial results.  Merging them inside merge_check would put up
+// to w * S * nsub dependent merges behind one warp (batch 1: ~1000), so they are merged here first, one warp
+// per (query, rank): the K best by (distance, offset) end up in the pair's first sub-slot.
+constexpr int SM_WARPS = 8;
+
+__global__ void __launch_bounds__(SM_WARPS * 32) stage_merge_kernel(RoundParams rp, int KP) {
+    __shared__ unsigned long long s_key[SM_WARPS][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long* key = s_key[warp];
+    const int K = rp.K, cap = rp.cap, metric = rp.metric, nseg = rp.S * rp.nsub;
+    const long npairs = (long)rp.n_active * rp.w;
+    for (long pidx = (long)blockIdx.x * SM_WARPS + warp; pidx < npairs; pidx += (long)gridDim.x * SM_WARPS) {
+        const long slot0 = pidx * nseg;
+        int total = 0;
+        bool any = false;
+        for (int sgm = 0; sgm < nseg; sgm += 32) {  // 32 counts per load
+            const int c = sgm + lane < nseg ? (rp.slot_cnt[slot0 + sgm + lane] & ~SLOT_SORTED) : 0;
+            any |= __any_sync(0xffffffffu, c > 0 && sgm + lane > 0);
+        }
+        if (!any) continue;  // nothing outside the first sub-slot
+        int c0 = min(rp.slot_cnt[slot0] & ~SLOT_SORTED, K);
+        for (int i = lane; i < KP; i += 32) {
+            unsigned long long kk = ~0ull;
+            if (i < c0) {
+                uint32_t o = f2ord(rp.cand_d[slot0 * cap + i]);
+                if (metric == METRIC_IP) o = ~o;
+                kk = ((unsigned long long)o << 32) | rp.cand_off[slot0 * cap + i];
+            }
+            key[i] = kk;
+        }
+        total = c0;
+        for (int sgm = 1; sgm < nseg; sgm++) {
+            const long sl = slot0 + sgm;
+            const int c = min(rp.slot_cnt[sl] & ~SLOT_SORTED, K);
+            if (c == 0) continue;
+            for (int i = lane; i < KP; i += 32) {  // second run reversed: the 2 KP keys form a bitonic sequence
+                unsigned long long kk = ~0ull;
+                if (i < c) {
+                    uint32_t o = f2ord(rp.cand_d[sl * cap + i]);
+                    if (metric == METRIC_IP) o = ~o;
+                    kk = ((unsigned long long)o << 32) | rp.cand_off[sl * cap + i];
+                }
+                key[2 * KP - 1 - i] = kk;
+            }
+            __syncwarp();
+            for (int stride = KP; stride > 0; stride >>= 1) {
+                for (int t = lane; t < KP; t += 32) {
+                    const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                    const unsigned long long x = key[lo], y = key[hi];
+                    if (x > y) {
+                        key[lo] = y;
+                        key[hi] = x;
+                    }
+                }
+                __syncwarp();
+            }
+            total = min(K, total + c);
+            if (lane == 0) rp.slot_cnt[sl] = 0;
+        }
+        __syncwarp();
+        for (int i = lane; i < total; i += 32) {
+            const unsigned long long kk = key[i];
+            uint32_t o = (uint32_t)(kk >> 32);
+            if (metric == METRIC_IP) o = ~o;
+            rp.cand_d[slot0 * cap + i] = ord2f(o);
+            rp.cand_off[slot0 * cap + i] = (unsigned)(kk & 0xffffffffu);
+        }
+        if (lane == 0) rp.slot_cnt[slot0] = total | SLOT_SORTED;
+        __syncwarp();
+    }
+}
+
+void launch_stage_merge(const RoundParams& rp, int num_sms, cudaStream_t s) {
+    const long npairs = (long)rp.n_active * rp.w;
+    if (npairs == 0 || rp.S * rp.nsub <= 1) return;
+    int KP = 16;
+    while (KP < rp.K) KP <<= 1;
+    const unsigned blocks = (unsigned)std::min<long>((npairs + SM_WARPS - 1) / SM_WARPS, (long)num_sms * 8);
+    stage_merge_kernel<<<blocks, SM_WARPS * 32, 0, s>>>(rp, KP);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_slot_sort(const RoundParams& rp, int num_sms, cudaStream_t s) {
+    const long nslots = (long)rp.n_active * rp.w * rp.S * rp.nsub;
+    if (nslots == 0) return;
+    AUNCEL_CHECK(rp.cap <= SS_MAX, "slot capacity too large");
+    const unsigned blocks = (unsigned)std::min<long>((nslots + SS_WARPS * 32 - 1) / (SS_WARPS * 32), (long)num_sms * 8);
+    slot_sort_kernel<<<blocks, SS_WARPS * 32, 0, s>>>(rp, nslots);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 // --------------------------------------------------------------------------- merge + check
 constexpr int MC_WARPS = 4;
 constexpr int MC_INSERT_MAX = 8;  // slots with at most this many candidates are merged by insertion
@@ -171,6 +351,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
     const float* dtb = tp.dtb ? tp.dtb + (long)q * tp.max_num : nullptr;
 
     unsigned nzmask = 0;
+    int grp_base = -1, cnt_grp = 0, flg_grp = 0;  // slot counts / redo flags of the current group of 32 stages
     // cur_num (IVF_pro.cpp:258-291) reads only the first query_topk entries of the sorted heap, the
     // boundary distances and the trace of `ind`: its value is reused until one of them changes
     int cached_ind = -1, topq_dirty = 1;
@@ -181,32 +362,156 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
         if (stage > bound) break;
         // ---- merge the candidates of probe rank stage-1 (all segments)
         const int nseg = rp.S * rp.nsub;
-        if (nseg == 1) {
-            // 32 slot counts per coalesced load; a decided query has nothing to do at a stage
-            // without candidates (the tune block cannot change its state any more, :615-632)
-            if ((p_rel & 31) == 0) {
-                const int pl = p_rel + lane;
-                const int cv = pl < rp.w ? rp.slot_cnt[(long)a * rp.w + pl] : 0;
-                nzmask = __ballot_sync(0xffffffffu, cv > 0);
+        if (decided && tp.mode == 1 && nseg == 1 && stage < bound) {
+            // ---- bulk path.  The stop stage of this query is known, the tune block no longer runs (:615-632),
+            // so the stages before the last one only merge: their candidates are gathered (up to KP at a time),
+            // ordered by (distance, arrival) -- arrival = (rank, offset), which is what one merge per stage
+            // would produce -- and merged in one go.  The last stage takes the regular path (break / profile).
+            const int p_end = min(rp.w, bound - rp.r0 - 1);  // stages [p_rel, p_end) are < bound
+            int T = 0, p = p_rel;
+            int cnt_l = 0, flg_l = 0;
+            bool stop = false;
+            auto flush = [&]() {
+                if (T == 0) return;
+                // candidate keys (ord << 32 | KP + arrival) are in sm.key[KP .. KP + T): sort them descending
+                // over the whole upper half (pads = largest first), the lower half gets the held results
+                for (int i = KP + T + lane; i < 2 * KP; i += 32) sm.key[i] = ~0ull;
+                __syncwarp();
+                for (int size = 2; size <= KP; size <<= 1)
+                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                        for (int t = lane; t < KP / 2; t += 32) {
+                            const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                            const bool down = ((lo & size) == 0);  // descending overall
+                            const unsigned long long x = sm.key[KP + lo], y = sm.key[KP + hi];
+                            if ((x < y) == down) {
+                                sm.key[KP + lo] = y;
+                                sm.key[KP + hi] = x;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                for (int i = lane; i < KP; i += 32) {
+                    unsigned long long k1 = ~0ull;
+                    if (i < rcnt) {
+                        uint32_t o = f2ord(sm.Rd[i]);
+                        if (metric == METRIC_IP) o = ~o;
+                        k1 = ((unsigned long long)o << 32) | (unsigned)i;
+                    }
+                    sm.key[i] = k1;
+                }
+                __syncwarp();
+#pragma unroll 1
+                for (int stride = KP; stride > 0; stride >>= 1) {
+                    for (int t = lane; t < KP; t += 32) {
+                        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                        const unsigned long long x = sm.key[lo], y = sm.key[hi];
+                        if (x > y) {
+                            sm.key[lo] = y;
+                            sm.key[hi] = x;
+                        }
+                    }
+                    __syncwarp();
+                }
+                rcnt = min(K, rcnt + T);
+                for (int i = lane; i < KP; i += 32) {
+                    if (i < rcnt) {
+                        const unsigned long long k = sm.key[i];
+                        uint32_t o = (uint32_t)(k >> 32);
+                        if (metric == METRIC_IP) o = ~o;
+                        const unsigned idx = (unsigned)(k & 0xffffffffu);
+                        sm.Rd[i] = ord2f(o);
+                        sm.code[cur ^ 1][i] = idx < (unsigned)KP ? sm.code[cur][idx] : sm.ccode[idx - KP];
+                    } else {
+                        sm.Rd[i] = neut;
+                    }
+                }
+                cur ^= 1;
+                T = 0;
+                __syncwarp();
+            };
+            while (p < p_end && !stop) {
+                if (p == p_rel || (p & 31) == 0) {
+                    const int pl = (p & ~31) + lane;
+                    cnt_l = pl < rp.w ? rp.slot_cnt[(long)a * rp.w + pl] : 0;
+                    flg_l = (pl < rp.w && rp.pair_flag) ? rp.pair_flag[(long)a * rp.w + pl] : 0;
+                }
+                // next stage with candidates in this group of 32
+                const unsigned nz = __ballot_sync(0xffffffffu, (cnt_l & ~SLOT_SORTED) > 0) & (~0u << (p & 31));
+                const int grp_end = min(p_end, (p & ~31) + 32);
+                if (nz == 0 || (p & ~31) + (__ffs(nz) - 1) >= grp_end) {
+                    p = grp_end;
+                    continue;
+                }
+                p = (p & ~31) + (__ffs(nz) - 1);
+                const int raw = __shfl_sync(0xffffffffu, cnt_l, p & 31);
+                const int flg = __shfl_sync(0xffffffffu, flg_l, p & 31);
+                if (flg || !(raw & SLOT_SORTED)) {  // redone pair / unordered slot: regular path
+                    stop = true;
+                    break;
+                }
+                const int c = min(raw & ~SLOT_SORTED, K);
+                if (T + c > KP) flush();
+                const long slot = (long)a * rp.w + p;
+                for (int i = lane; i < c; i += 32) {
+                    uint32_t o = f2ord(rp.cand_d[slot * rp.cap + i]);
+                    if (metric == METRIC_IP) o = ~o;
+                    sm.key[KP + T + i] = ((unsigned long long)o << 32) | (unsigned)(KP + T + i);
+                    sm.ccode[T + i] = ((unsigned long long)(unsigned)(rp.r0 + p) << 32) | rp.cand_off[slot * rp.cap + i];
+                }
+                T += c;
+                p++;
             }
-            if (!((nzmask >> (p_rel & 31)) & 1u) && decided && stage < bound) continue;
+            flush();
+            if (p > p_rel) {
+                p_rel = p - 1;  // the loop increment moves on to stage p
+                grp_base = -1;  // (the bulk path keeps its own group registers)
+                continue;
+            }
         }
-        for (int seg = 0; seg < nseg; seg++) {
-            const long slot = ((long)a * rp.w + p_rel) * nseg + seg;
-            const int raw_cnt = rp.slot_cnt[slot];
-            const int c = min(raw_cnt & ~SLOT_SORTED, K);
+        // One slot per pair (tensor-core rounds; exact rounds after stage_merge_kernel): the counts and
+        // redo flags of 32 consecutive stages come from one coalesced load each, so a stage costs no
+        // dependent global load of its own unless it has candidates.
+        const bool single = nseg == 1 || rp.merged;
+        int raw0 = 0, flagged = 0;
+        if (single) {
+            if ((p_rel & ~31) != grp_base) {
+                grp_base = p_rel & ~31;
+                const int pl = grp_base + lane;
+                cnt_grp = pl < rp.w ? rp.slot_cnt[((long)a * rp.w + pl) * nseg] : 0;
+                flg_grp = (pl < rp.w && rp.pair_flag) ? rp.pair_flag[(long)a * rp.w + pl] : 0;
+                nzmask = __ballot_sync(0xffffffffu, cnt_grp > 0);
+            }
+            raw0 = __shfl_sync(0xffffffffu, cnt_grp, p_rel & 31);
+            flagged = __shfl_sync(0xffffffffu, flg_grp, p_rel & 31);
+            // a decided query has nothing to do at a stage without candidates (the tune block cannot change
+            // its state any more, :615-632)
+            if (raw0 == 0 && decided && stage < bound) continue;
+        }
+        // flagged pair of a tensor-core round: its candidates are the exact redo's, in the compact pool
+        const long pidx = (long)a * rp.w + p_rel;
+        const bool redo = rp.redo_ord != nullptr && (single ? flagged != 0 : (rp.pair_flag != nullptr && rp.pair_flag[pidx] != 0));
+        const int nseg_s = (single && raw0 == 0) ? 0 : redo ? 4 : (rp.merged ? 1 : nseg);  // merged: one slot per pair
+        const int cap = redo ? K : rp.cap;
+        float* const cand_d = redo ? rp.redo_d : rp.cand_d;
+        unsigned* const cand_off = redo ? rp.redo_off : rp.cand_off;
+        const int* const slot_cnt = redo ? rp.redo_cnt : rp.slot_cnt;
+        for (int seg = 0; seg < nseg_s; seg++) {
+            const long slot = redo ? (long)rp.redo_ord[pidx] * 4 + seg : pidx * nseg + seg;
+            const int raw_cnt = (single && !redo) ? raw0 : slot_cnt[slot];
+            const int rc = min(raw_cnt & ~SLOT_SORTED, cap);  // entries present (unsorted wide slots: up to cap)
+            const int c = min(rc, K);                          // entries that can matter
             if (c == 0) continue;
             const int rcnt_before = rcnt;
             const float kth_before = (qk_i >= 1 && rcnt >= qk_i) ? sm.Rd[qk_i - 1] : neut;
-            if (c <= MC_INSERT_MAX) {
+            if (rc <= MC_INSERT_MAX) {
                 // A handful of candidates (the usual case after the tensor-core filter): insert them one
                 // by one into the sorted top-k instead of a 2*KP bitonic merge.  A candidate goes behind
                 // every held value <= it, like the (value, arrival) order of the merge below.
                 unsigned long long kk = ~0ull;
-                if (lane < c) {
-                    uint32_t o = f2ord(rp.cand_d[slot * K + lane]);
+                if (lane < rc) {
+                    uint32_t o = f2ord(cand_d[slot * cap + lane]);
                     if (metric == METRIC_IP) o = ~o;
-                    kk = ((unsigned long long)o << 32) | rp.cand_off[slot * K + lane];
+                    kk = ((unsigned long long)o << 32) | cand_off[slot * cap + lane];
                 }
                 if (!(raw_cnt & SLOT_SORTED)) {
 #pragma unroll
@@ -274,12 +579,12 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
             if (!(raw_cnt & SLOT_SORTED)) {
                 // rerank_kernel (tensor-core rounds) appends survivors in arrival order and the exact
                 // scan hands over short lists as they are: order them by (distance, offset), in place
-                if (c <= 32) {
+                if (rc <= 32) {
                     unsigned long long kk = ~0ull;
-                    if (lane < c) {
-                        uint32_t o = f2ord(rp.cand_d[slot * K + lane]);
+                    if (lane < rc) {
+                        uint32_t o = f2ord(cand_d[slot * cap + lane]);
                         if (metric == METRIC_IP) o = ~o;
-                        kk = ((unsigned long long)o << 32) | rp.cand_off[slot * K + lane];
+                        kk = ((unsigned long long)o << 32) | cand_off[slot * cap + lane];
                     }
 #pragma unroll
                     for (int k2 = 2; k2 <= 32; k2 <<= 1)
@@ -293,24 +598,27 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
                     if (lane < c) {
                         uint32_t o = (uint32_t)(kk >> 32);
                         if (metric == METRIC_IP) o = ~o;
-                        rp.cand_d[slot * K + lane] = ord2f(o);
-                        rp.cand_off[slot * K + lane] = (unsigned)(kk & 0xffffffffu);
+                        cand_d[slot * cap + lane] = ord2f(o);
+                        cand_off[slot * cap + lane] = (unsigned)(kk & 0xffffffffu);
                     }
                     __syncwarp();
                 } else {
-                    for (int i = lane; i < KP; i += 32) {
+                    // wide slots (first tensor-core round) hold up to cap <= 2 KP survivors: sort them all,
+                    // the K best go on
+                    const int P = rc <= KP ? KP : 2 * KP;
+                    for (int i = lane; i < P; i += 32) {
                         unsigned long long kk = ~0ull;
-                        if (i < c) {
-                            uint32_t o = f2ord(rp.cand_d[slot * K + i]);
+                        if (i < rc) {
+                            uint32_t o = f2ord(cand_d[slot * cap + i]);
                             if (metric == METRIC_IP) o = ~o;
-                            kk = ((unsigned long long)o << 32) | rp.cand_off[slot * K + i];
+                            kk = ((unsigned long long)o << 32) | cand_off[slot * cap + i];
                         }
                         sm.key[i] = kk;
                     }
                     __syncwarp();
-                    for (int size = 2; size <= KP; size <<= 1)
+                    for (int size = 2; size <= P; size <<= 1)
                         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                            for (int t = lane; t < KP / 2; t += 32) {
+                            for (int t = lane; t < P / 2; t += 32) {
                                 int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
                                 bool up = ((lo & size) == 0);
                                 unsigned long long x = sm.key[lo], y = sm.key[hi];
@@ -325,8 +633,8 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
                         unsigned long long kk = sm.key[i];
                         uint32_t o = (uint32_t)(kk >> 32);
                         if (metric == METRIC_IP) o = ~o;
-                        rp.cand_d[slot * K + i] = ord2f(o);
-                        rp.cand_off[slot * K + i] = (unsigned)(kk & 0xffffffffu);
+                        cand_d[slot * cap + i] = ord2f(o);
+                        cand_off[slot * cap + i] = (unsigned)(kk & 0xffffffffu);
                     }
                     __syncwarp();
                 }
@@ -339,10 +647,10 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
                     k1 = ((unsigned long long)o << 32) | (unsigned)i;
                 }
                 if (i < c) {
-                    uint32_t o = f2ord(rp.cand_d[slot * K + i]);
+                    uint32_t o = f2ord(cand_d[slot * cap + i]);
                     if (metric == METRIC_IP) o = ~o;
                     k2 = ((unsigned long long)o << 32) | (unsigned)(KP + i);
-                    sm.ccode[i] = ((unsigned long long)(unsigned)(stage - 1) << 32) | rp.cand_off[slot * K + i];
+                    sm.ccode[i] = ((unsigned long long)(unsigned)(stage - 1) << 32) | cand_off[slot * cap + i];
                 }
                 sm.key[i] = k1;
                 sm.key[2 * KP - 1 - i] = k2;
@@ -379,7 +687,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
             if (tp.mode == 1 && qk_i >= 1) {
                 // did a candidate enter the first query_topk positions?  (its best one must beat the
                 // old query_topk-th value; an equal value leaves the sorted values unchanged)
-                const float best = rp.cand_d[slot * K];
+                const float best = cand_d[slot * cap];
                 if (rcnt_before < qk_i || (metric == METRIC_L2 ? best < kth_before : best > kth_before)) topq_dirty = 1;
             }
         }

@@ -26,6 +26,10 @@ void launch_init_state(const RoundParams& rp, const TuneParams& tp, const unsign
 void launch_set_online(int metric, long nlist, long n, const float* cdis, const int* ckeys,
                        const float* interdis, const float* arcos, int arcos_size, float* dtb,
                        int max_num, int* ctl, cudaStream_t s);
+// merges the S * nsub partial results of every (query, rank) pair into the pair's first sub-slot
+void launch_stage_merge(const RoundParams& rp, int num_sms, cudaStream_t s);
+// orders the unsorted slots of a tensor-core round by (distance, offset), keeps the K best of each
+void launch_slot_sort(const RoundParams& rp, int num_sms, cudaStream_t s);
 void launch_merge_check(const RoundParams& rp, const TuneParams& tp, cudaStream_t s);
 void launch_compact_active(const RoundParams& rp, int r1, int* active_out, int* h_ctl_pinned,
                            cudaStream_t s);

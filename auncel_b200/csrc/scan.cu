@@ -108,7 +108,8 @@ __global__ void plan_fill_kernel(RoundParams rp) {
     if (rp.list_off[l + 1] == rp.list_off[l]) return;
     if (rp.filtered) {
         if (!rp.pair_flag[idx]) return;
-        rp.slot_cnt[idx] = 0;  // the exact scan rewrites this slot
+        if (rp.redo_ord) rp.redo_ord[idx] = atomicAdd(&rp.ctl[CTL_REDO_N], 1);  // compact redo pool
+        else rp.slot_cnt[idx] = 0;  // the exact scan rewrites this slot
     }
     int pos = rp.list_pair_off[l] + atomicAdd(&rp.list_cursor[l], 1);
     rp.pairs[pos] = ((unsigned long long)(unsigned)a << 32) | (unsigned)p_rel;
@@ -134,6 +135,7 @@ void launch_plan(const RoundParams& rp, cudaStream_t s) {
     long tot = (long)rp.n_active * rp.w;
     CUDA_CHECK(cudaMemsetAsync(rp.list_cnt, 0, rp.nlist * sizeof(int), s));
     if (!rp.filtered) CUDA_CHECK(cudaMemsetAsync(rp.slot_cnt, 0, (size_t)tot * rp.S * rp.nsub * sizeof(int), s));
+    if (rp.filtered && rp.redo_ord) CUDA_CHECK(cudaMemsetAsync(rp.ctl + CTL_REDO_N, 0, sizeof(int), s));
     unsigned blocks = (unsigned)((tot + 255) / 256);
     plan_count_kernel<<<blocks, 256, 0, s>>>(rp);
     plan_offsets_kernel<<<1, 1024, 0, s>>>(rp);
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
             if (lane < Qt) {
                 unsigned long long pr = rp.pairs[pair0 + lane];
                 int a = (int)(pr >> 32), p_rel = (int)(pr & 0xffffffffu);
-                slot = (a * rp.w + p_rel) * rp.S + seg;
+                slot = rp.redo_ord ? rp.redo_ord[a * rp.w + p_rel] : (a * rp.w + p_rel) * rp.S + seg;
                 tau = rp.st.tau[rp.active[a]];
             }
             const int nvec = v_end - v_begin;
@@ -556,8 +558,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
                         key = warp_sort_reg(key, lane);
                         const int c = min(cnt[i], K);
                         if (lane < c) {
-                            rp.cand_d[sl * K + lane] = key_dist<METRIC>(key);
-                            rp.cand_off[sl * K + lane] = (unsigned)(key & 0xffffffffu);
+                            rp.cand_d[sl * rp.cap + lane] = key_dist<METRIC>(key);
+                            rp.cand_off[sl * rp.cap + lane] = (unsigned)(key & 0xffffffffu);
                         }
                         if (lane == 0) rp.slot_cnt[sl] = c | SLOT_SORTED;
                     } else {
@@ -567,8 +569,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
                         if (sorted) compact<METRIC>(buf, cnt[i], tau[i], K, lane);
                         for (int t = lane; t < cnt[i]; t += 32) {
                             unsigned long long key = buf[t];
-                            rp.cand_d[sl * K + t] = key_dist<METRIC>(key);
-                            rp.cand_off[sl * K + t] = (unsigned)(key & 0xffffffffu);
+                            rp.cand_d[sl * rp.cap + t] = key_dist<METRIC>(key);
+                            rp.cand_off[sl * rp.cap + t] = (unsigned)(key & 0xffffffffu);
                         }
                         if (lane == 0) rp.slot_cnt[sl] = cnt[i] | (sorted ? SLOT_SORTED : 0);
                     }

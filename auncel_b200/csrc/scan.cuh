@@ -6,7 +6,8 @@ namespace auncel {
 
 // control block slots (device ints, mirrored to pinned host memory once per round)
 enum { CTL_N_ACTIVE = 0, CTL_TOTAL_TILES = 1, CTL_TILE_COUNTER = 2, CTL_TOTAL_PAIRS = 3,
-       CTL_ERR = 4, CTL_NFIX = 5, CTL_NCAND = 6, CTL_OVERFLOW = 7, CTL_MIN_RCNT = 8, CTL_NOT_FULL = 9, CTL_MERGE_NEXT = 10, CTL_SIZE = 16 };
+       CTL_ERR = 4, CTL_NFIX = 5, CTL_NCAND = 6, CTL_OVERFLOW = 7, CTL_MIN_RCNT = 8, CTL_NOT_FULL = 9, CTL_MERGE_NEXT = 10,
+       CTL_REDO_N = 11, CTL_SIZE = 16 };
 
 // per-query running state, SoA, carved from IvfIndex::state
 struct QState {
@@ -59,6 +60,7 @@ struct RoundParams {
     const float* cdis;    // n x nlist ranked centroid distances
     long n;
     int K;
+    int cap;              // entries per candidate slot (>= K; the first tensor-core round uses wider slots)
     // round
     const int* active;    // n_active -> query
     int n_active;
@@ -66,9 +68,18 @@ struct RoundParams {
     int qt;               // queries per scan tile this round: 32 / nsub
     int nsub;             // sub-slots per (query, rank, segment) = row subsets of the scan tile (1, 2 or 4)
     int defer_sort;       // 1: the exact scan may hand over <= K candidates unsorted (many queries: merge_check has the warps)
+    int merged;           // 1: stage_merge_kernel reduced every pair's S * nsub sub-slots to its first one
     int unsorted;         // (logging)  1: slots were filled by rerank_kernel in arrival order (tensor-core rounds)
     int* pair_flag;       // tensor-core rounds: per slot, 1 = overflowed -> redo this pair with the exact scan
     int filtered;         // plan only the flagged pairs
+    // exact redo of the flagged pairs of a tensor-core round: they are few and scattered, so they are
+    // scanned with the narrow (row-split) tiles into a compact pool of their own -- flagged pair ->
+    // redo_ord[pair] -> 4 sub-slots of K entries.  The scan launch of the redo has cand_d/cand_off/slot_cnt
+    // pointing at that pool; merge_check reads it through the redo_* members.
+    int* redo_ord;
+    float* redo_d;
+    unsigned* redo_off;
+    int* redo_cnt;
     // plan
     int* list_cnt;
     int* list_pair_off;   // nlist + 1
@@ -79,7 +90,7 @@ struct RoundParams {
     int* ctl;
     unsigned long long* round_work;  // [0] sum of |list| over the round's pairs (algorithmic distance evaluations),
                                      // [1] vectors of the distinct lists touched, [2] vectors staged (one pass per query tile)
-    // pool: slot = ((a * w + p_rel) * S + seg) * nsub + sub, K entries each
+    // pool: slot = ((a * w + p_rel) * S + seg) * nsub + sub, `cap` entries each
     float* cand_d;
     unsigned* cand_off;
     int* slot_cnt;

@@ -330,6 +330,9 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                 break;
             }
             const int nblk = mt->nblk, L = mt->L, pair0 = mt->pair0;
+            // once the survivor list is full the round is redone anyway: stop counting (checked once per
+            // tile), so the signed counter can never wrap however many pairs pass a loose threshold
+            const bool dead = *reinterpret_cast<volatile int*>(&rp.ctl[CTL_OVERFLOW]) < 0;
             const int ncg = min(N, (mt->Qt + 31) / 32 * 32) / 32;
             const long long row0 = mt->row0;
             for (int blk = 0; blk < nblk; blk++, blkc++) {
@@ -356,17 +359,29 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                             pass = __fmaf_rn(c.x, snv, dot) > c.y;
                         hits |= (pass ? 1u : 0u) << j;
                     }
-                    // once the survivor list is full the round is redone anyway: stop counting, so the
-                    // (signed) counter can never wrap however many pairs pass a loose threshold
-                    if (!valid || *reinterpret_cast<volatile int*>(&rp.ctl[CTL_OVERFLOW]) < 0) hits = 0;
-                    while (hits) {
-                        const int j = __ffs(hits) - 1;
-                        hits &= hits - 1;
-                        const int pos = atomicAdd(&rp.ctl[CTL_NCAND], 1);
-                        if ((unsigned)pos < (unsigned)ta.cand_cap)
-                            ta.cand[pos] = ((unsigned long long)(unsigned)(pair0 + cg * 32 + j) << 32) | (unsigned)v;
-                        else
-                            rp.ctl[CTL_OVERFLOW] = -(1 << 30);  // survivor list full: the whole round is redone
+                    if (!valid || dead) hits = 0;
+                    if (__any_sync(0xffffffffu, hits != 0)) {
+                        // one atomic per warp and chunk: lane offsets by an inclusive scan of the hit counts
+                        const int mine = __popc(hits);
+                        int incl = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += up;
+                        }
+                        int base = 0;
+                        if (lane == 31) base = atomicAdd(&rp.ctl[CTL_NCAND], incl);
+                        base = __shfl_sync(0xffffffffu, base, 31);
+                        int pos = base + incl - mine;
+                        while (hits) {
+                            const int j = __ffs(hits) - 1;
+                            hits &= hits - 1;
+                            if ((unsigned)pos < (unsigned)ta.cand_cap)
+                                ta.cand[pos] = ((unsigned long long)(unsigned)(pair0 + cg * 32 + j) << 32) | (unsigned)v;
+                            else
+                                rp.ctl[CTL_OVERFLOW] = -(1 << 30);  // survivor list full: the whole round is redone
+                            pos++;
+                        }
                     }
                 }
                 tc_fence_before();
@@ -411,11 +426,11 @@ __global__ void rerank_kernel(RoundParams rp, TcArgs ta) {
         if (METRIC == METRIC_L2 ? dist < tau : dist > tau) {
             const long slot = (long)a * rp.w + p_rel;  // S == nsub == 1
             const int o = atomicAdd(&rp.slot_cnt[slot], 1);
-            if (o < rp.K) {
-                rp.cand_d[slot * rp.K + o] = dist;
-                rp.cand_off[slot * rp.K + o] = v;
+            if (o < rp.cap) {
+                rp.cand_d[slot * rp.cap + o] = dist;
+                rp.cand_off[slot * rp.cap + o] = v;
             } else {
-                rp.pair_flag[slot] = 1;  // more than K vectors of this list beat tau: exact scan redoes the pair
+                rp.pair_flag[slot] = 1;  // more vectors of this list beat tau than a slot holds: exact scan redoes the pair
                 atomicAdd(&rp.ctl[CTL_OVERFLOW], 1);
             }
         }
@@ -431,17 +446,19 @@ __global__ void tc_audit_kernel(RoundParams tc, const float* __restrict__ ex_d, 
     const int lane = threadIdx.x & 31;
     if (slot >= (long)tc.n_active * tc.w) return;
     if (tc.pair_flag[slot]) return;  // more than K survivors: the exact scan rewrites this slot anyway
-    const int K = tc.K;
+    // the exact rescan keeps the K best candidates below tau, the filter path everything below tau (up to
+    // the slot capacity): every exact entry must be present, and the counts must agree up to K
+    const int K = tc.K, cap = tc.cap;
     const int c1 = tc.slot_cnt[slot] & ~SLOT_SORTED, c2 = ex_cnt[slot] & ~SLOT_SORTED;
-    bool bad = c1 != c2;
+    bool bad = min(c1, K) != c2;
     if (!bad)
         for (int i = lane; i < c2; i += 32) {
             const float dv = ex_d[slot * K + i];
             const unsigned ov = ex_off[slot * K + i];
             bool found = false;
             for (int j = 0; j < c1; j++)
-                found |= (tc.cand_off[slot * K + j] == ov) &&
-                         (__float_as_uint(tc.cand_d[slot * K + j]) == __float_as_uint(dv));
+                found |= (tc.cand_off[slot * cap + j] == ov) &&
+                         (__float_as_uint(tc.cand_d[slot * cap + j]) == __float_as_uint(dv));
             bad |= !found;
         }
     bad = __any_sync(0xffffffffu, bad);

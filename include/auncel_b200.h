@@ -184,7 +184,7 @@ int auncel_index_get_stats(const AuncelIndex* idx, double* out32);
  * compare the candidate slots */
 int auncel_index_set_option(AuncelIndex* idx, const char* name, int value);
 
-/* scratch budget for per-round candidate pools, bytes (default 4 GiB) */
+/* scratch budget for per-round candidate pools, bytes (default 16 GiB) */
 int auncel_index_set_pool_budget(AuncelIndex* idx, size_t bytes);
 
 /* merge_tables (IndexShards.cpp:44-105): k-way merge of nshard sorted (n x k) result tables

@@ -64,7 +64,7 @@ def test_fixed_nprobe_properties(big):
     # different scratch budget -> different round schedule, same bits
     ix.set_pool_budget(64 << 20)
     D1, I1 = _fixed(ix, q, 64)
-    ix.set_pool_budget(4 << 30)
+    ix.set_pool_budget(16 << 30)
     assert np.array_equal(D1, D) and np.array_equal(I1, I)
 
 
