@@ -57,6 +57,7 @@ SYMBOLS = {
     "auncel_index_range_search": (C.c_int, [_h, C.c_int64, _f, C.c_float, C.c_int64, _l]),
     "auncel_index_range_search_results": (C.c_int, [_h, _f, _l]),
     "auncel_index_get_stats": (C.c_int, [_h, _d]),
+    "auncel_index_get_round_stats": (C.c_int, [_h, C.c_int, _d, C.POINTER(C.c_int)]),
     "auncel_index_set_pool_budget": (C.c_int, [_h, C.c_size_t]),
     "auncel_index_set_option": (C.c_int, [_h, C.c_char_p, C.c_int]),
     "auncel_merge_tables": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, _f, _l, _l, _f, _l]),

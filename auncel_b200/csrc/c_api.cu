@@ -593,6 +593,15 @@ int auncel_index_get_stats(const AuncelIndex* idx, double* out8) {
     return 0;
 }
 
+int auncel_index_get_round_stats(const AuncelIndex* idx, int max_rounds, double* out, int* n_rounds) {
+    const auto& rs = idx->ix.round_stats;
+    const int n = (int)std::min<size_t>(rs.size(), (size_t)std::max(max_rounds, 0));
+    for (int r = 0; r < n; r++)
+        for (int j = 0; j < 10; j++) out[r * 10 + j] = rs[r][j];
+    if (n_rounds) *n_rounds = (int)rs.size();
+    return 0;
+}
+
 int auncel_index_set_option(AuncelIndex* idx, const char* name, int value) {
     API_TRY
     std::string n(name ? name : "");

@@ -187,6 +187,9 @@ struct IvfIndex {
     SearchStats stats;
     bool debug_rounds = false;
     std::vector<std::array<int, 6>> round_log;
+    // per round of the last search: r0, w, active queries, 1 = tensor-core filter round, distance evaluations,
+    // vectors of the distinct lists touched, vectors staged, scan-phase ms, tc_filter_kernel ms, (reserved)
+    std::vector<std::array<double, 10>> round_stats;
     int num_sms = 148;
 
     IvfIndex(int d, long nlist, int metric, int device);

@@ -407,6 +407,8 @@ void IvfIndex::search(const QueryBatch& qb) {
     std::vector<uint64_t> round_uniq, round_staged;
     std::vector<int> tc_round_of;     // per round: index of its tensor-core event pair, or -1
     std::vector<uint64_t> round_ndis;
+    std::vector<std::array<double, 3>> round_meta;  // r0, w, active queries
+    round_stats.clear();
     rp.list_cnt = list_cnt.ensure(nlist);
     rp.list_pair_off = list_pair_off.ensure(nlist + 1);
     rp.list_tile_off = list_tile_off.ensure(nlist + 1);
@@ -687,6 +689,7 @@ void IvfIndex::search(const QueryBatch& qb) {
         launch_compact_active(rp, r0 + (int)w, act_nxt, h_ctl.p, stream);
         CUDA_CHECK(cudaStreamSynchronize(stream));
         tc_round_of.push_back(tc_idx);
+        round_meta.push_back({(double)r0, (double)w, (double)rp.n_active});
         round_ndis.push_back(h_round_work.p[0]);
         round_uniq.push_back(h_round_work.p[1]);
         round_staged.push_back(h_round_work.p[2]);
@@ -723,9 +726,12 @@ void IvfIndex::search(const QueryBatch& qb) {
         float t = 0.f;
         CUDA_CHECK(cudaEventElapsedTime(&t, scan_ev[2 * r], scan_ev[2 * r + 1]));
         scan_ms_total += t;
-        if (tc_round_of[r] >= 0) {
-            float tt = 0.f;
+        float tt = 0.f;
+        if (tc_round_of[r] >= 0)
             CUDA_CHECK(cudaEventElapsedTime(&tt, tc_ev[2 * tc_round_of[r]], tc_ev[2 * tc_round_of[r] + 1]));
+        round_stats.push_back({round_meta[r][0], round_meta[r][1], round_meta[r][2], tc_round_of[r] >= 0 ? 1.0 : 0.0,
+                               (double)round_ndis[r], (double)round_uniq[r], (double)round_staged[r], (double)t, (double)tt, 0.0});
+        if (tc_round_of[r] >= 0) {
             stats.tc_ms += tt;
             stats.tc_ndis += round_ndis[r];
             stats.tc_uniq += round_uniq[r];

@@ -322,7 +322,10 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
     // thresholds shared by the RSPLIT warps that scan different rows for the same query: a warp
     // that has K candidates publishes its K-th best, the others filter with the tightest value.
     // Ring of 8 tiles (> STAGES, the furthest a warp can run ahead), reset by the producer.
-    __shared__ unsigned s_tau[8][SCAN_QT];
+    constexpr int TAU_RING = 8;
+    static_assert(TAU_RING > STAGES + 1, "a consumer can run at most STAGES stages (hence < STAGES + 1 tiles) ahead "
+                                         "of the slowest one: the threshold ring must be deeper than that");
+    __shared__ unsigned s_tau[TAU_RING][SCAN_QT];
     unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned long long* cand = reinterpret_cast<unsigned long long*>(smem + (size_t)STAGES * STAGE_BYTES);
 

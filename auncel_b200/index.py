@@ -236,6 +236,14 @@ class IndexIVFFlat:
                          "simt_uniq", "simt_staged", "tc_audit_bad", "tc_audit_slots", "tc_audit_cands"],
                         [float(v) for v in out]))
 
+    def round_stats(self):
+        """per round of the last search: dicts with r0, w, active, tc, ndis, uniq, staged, scan_ms, tc_ms"""
+        out = (C.c_double * (64 * 10))()
+        n = C.c_int(0)
+        lib().auncel_index_get_round_stats(self.h, 64, out, C.byref(n))
+        keys = ["r0", "w", "active", "tc", "ndis", "uniq", "staged", "scan_ms", "tc_ms"]
+        return [dict(zip(keys, [float(out[r * 10 + j]) for j in range(9)])) for r in range(min(n.value, 64))]
+
     def set_option(self, name, value):
         _ck(lib().auncel_index_set_option(self.h, name.encode(), int(value)))
 

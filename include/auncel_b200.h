@@ -178,6 +178,12 @@ int auncel_index_range_search_results(AuncelIndex* idx, float* distances, int64_
  * out: 32 doubles */
 int auncel_index_get_stats(const AuncelIndex* idx, double* out32);
 
+/* Per round of the last search (a round = one window of probe ranks for all still-active queries), 10 doubles each:
+ * [0] first rank [1] window width [2] active queries [3] 1 = served by the tensor-core filter [4] distance
+ * evaluations [5] vectors of the distinct lists touched (compulsory HBM traffic / 4d bytes) [6] vectors staged into
+ * shared memory [7] scan-phase ms [8] tc_filter_kernel ms [9] reserved.  *n_rounds receives the number of rounds. */
+int auncel_index_get_round_stats(const AuncelIndex* idx, int max_rounds, double* out, int* n_rounds);
+
 /* engine switches (results never change): "tensor_core_filter" 0 off / 1 automatic / 2 whenever
  * every active query holds K results; "exact_ties" 0/1 replay of the reference's heap order for
  * equal centroid distances; "tc_audit" 0/1 (tests) redo every tensor-core round with the exact scan and
