@@ -198,29 +198,12 @@ rank_rows_kernel(int metric, const float* __restrict__ dis, long nlist, int P, f
 // the strided access patterns are then bank-conflict free.
 __device__ __forceinline__ int rr_sw(int i) { return i ^ (((i >> 4) & 7) << 1); }
 
+// The bitonic network on E keys per thread (T threads, P = T * E keys): compare-exchange distances below E stay
+// in registers, distances below 32 E go through warp shuffles, only the longer ones through shared memory.
 template <int E>
-__global__ void __launch_bounds__(1024)
-rank_rows_reg_kernel(int metric, const float* __restrict__ dis, long nlist, int P, float* __restrict__ out_dis,
-                     int* __restrict__ out_keys, int* __restrict__ tie0) {
-    extern __shared__ __align__(16) unsigned long long skey[];
-    __shared__ int s_tie;
-    const int t = threadIdx.x, T = blockDim.x, lane = t & 31;
-    if (t == 0) s_tie = 0x7fffffff;
-    const long q = blockIdx.x;
-    const float* row = dis + q * nlist;
-    const int base = t * E;
-    unsigned long long e[E];
-#pragma unroll
-    for (int r = 0; r < E; r++) {
-        const int i = base + r;
-        unsigned long long key = ~0ull;
-        if (i < nlist) {
-            uint32_t o = f2ord(row[i]);
-            if (metric == METRIC_IP) o = ~o;
-            key = ((unsigned long long)o << 32) | (unsigned)i;
-        }
-        e[r] = key;
-    }
+__device__ __forceinline__ void block_bitonic_sort(unsigned long long (&e)[E], unsigned long long* skey, int P, int t,
+                                                   int T) {
+    const int lane = t & 31, base = t * E;
     for (int size = 2; size <= P; size <<= 1) {
         int stride = size >> 1;
         if (stride >= 32 * E) {
@@ -283,7 +266,45 @@ rank_rows_reg_kernel(int metric, const float* __restrict__ dis, long nlist, int 
     for (int r = 0; r < E; r += 2)
         *reinterpret_cast<ulonglong2*>(&skey[rr_sw(base + r)]) = make_ulonglong2(e[r], e[r + 1]);
     __syncthreads();
+}
+
+// Full ranking.  qlist / sorted_upto (both nullable): "extension" launch -- block b serves query qlist[b]
+// (or b), does nothing if the query's row is already ranked up to `need_upto` (or completely), and otherwise
+// writes only the ranks >= sorted_upto[q]: the prefix a partial ranking (below) produced is kept as it is.
+template <int E>
+__global__ void __launch_bounds__(1024)
+rank_rows_reg_kernel(int metric, const float* __restrict__ dis, long nlist, int P, float* __restrict__ out_dis,
+                     int* __restrict__ out_keys, int* __restrict__ tie0, const int* __restrict__ qlist,
+                     int* __restrict__ sorted_upto, const int* __restrict__ qbound, int need_upto) {
+    extern __shared__ __align__(16) unsigned long long skey[];
+    __shared__ int s_tie;
+    const int t = threadIdx.x, T = blockDim.x;
+    const long q = qlist ? qlist[blockIdx.x] : blockIdx.x;
+    if (q < 0) return;
+    int start = 0;
+    if (sorted_upto) {
+        start = sorted_upto[q];
+        const int need = qbound ? min(need_upto, qbound[q] + 1) : need_upto;
+        if (start >= nlist || start >= need) return;
+    }
+    if (t == 0) s_tie = 0x7fffffff;
+    const float* row = dis + q * nlist;
+    const int base = t * E;
+    unsigned long long e[E];
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+        const int i = base + r;
+        unsigned long long key = ~0ull;
+        if (i < nlist) {
+            uint32_t o = f2ord(row[i]);
+            if (metric == METRIC_IP) o = ~o;
+            key = ((unsigned long long)o << 32) | (unsigned)i;
+        }
+        e[r] = key;
+    }
+    block_bitonic_sort<E>(e, skey, P, t, T);
     for (int i = t; i < nlist; i += T) {
+        if (i < start) continue;  // ranks a partial ranking (or nothing) already put in place
         const unsigned long long key = skey[rr_sw(i)];
         uint32_t o = (uint32_t)(key >> 32);
         if (metric == METRIC_IP) o = ~o;
@@ -292,7 +313,116 @@ rank_rows_reg_kernel(int metric, const float* __restrict__ dis, long nlist, int 
         if (i + 1 < nlist && (uint32_t)(skey[rr_sw(i + 1)] >> 32) == (uint32_t)(key >> 32)) atomicMin(&s_tie, i);
     }
     __syncthreads();
-    if (t == 0) tie0[q] = s_tie;
+    if (t == 0) {
+        // extension: an earlier tie (still pending) stays the first one
+        if (start == 0 || tie0[q] == 0x7fffffff) tie0[q] = s_tie;
+        if (sorted_upto) sorted_upto[q] = (int)nlist;
+    }
+}
+
+// Partial ranking for Auncel mode (nprobe = nlist): a query probes my_nprobe lists -- a few hundred of
+// thousands --, so only the M best centroids are ranked up front.  The M-th smallest key is found by a radix
+// select over the 32-bit order-preserving image of the distance (4 passes, 256-bin shared-memory histograms);
+// every centroid at or below it (ties included, so the cut never splits a run of equal distances) is
+// compacted and ranked by the same network.  sorted_upto[q] = number of ranks written; rows that need more
+// are completed by the extension launch of rank_rows_reg_kernel before the round that reads them.
+constexpr int RP_M = 1024, RP_T = 128, RP_E = 8;
+
+__global__ void __launch_bounds__(RP_T)
+rank_rows_partial_kernel(int metric, const float* __restrict__ dis, long nlist, float* __restrict__ out_dis,
+                         int* __restrict__ out_keys, int* __restrict__ tie0, int* __restrict__ sorted_upto) {
+    __shared__ __align__(16) unsigned long long skey[RP_M];
+    __shared__ int hist[256];
+    __shared__ int s_cnt, s_tie, s_digit, s_before;
+    const int t = threadIdx.x;
+    const long q = blockIdx.x;
+    const float* row = dis + q * nlist;
+    // ---- radix select of the RP_M-th smallest ord
+    uint32_t prefix = 0, mask = 0;
+    int remaining = RP_M;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = t; i < 256; i += RP_T) hist[i] = 0;
+        __syncthreads();
+        for (long i = t; i < nlist; i += RP_T) {
+            uint32_t o = f2ord(row[i]);
+            if (metric == METRIC_IP) o = ~o;
+            if ((o & mask) == prefix) atomicAdd(&hist[(o >> shift) & 255], 1);
+        }
+        __syncthreads();
+        if (t < 32) {  // one warp: 8 bins per lane, find the bin where the running count reaches `remaining`
+            int loc[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                loc[j] = hist[t * 8 + j];
+                sum += loc[j];
+            }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (t >= o) incl += up;
+            }
+            int before = incl - sum;
+            if (before < remaining && remaining <= incl) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (before < remaining && remaining <= before + loc[j]) {
+                        s_digit = t * 8 + j;
+                        s_before = before;
+                    }
+                    before += loc[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= (uint32_t)s_digit << shift;
+        mask |= 0xffu << shift;
+        remaining -= s_before;
+        __syncthreads();
+    }
+    const uint32_t pivot = prefix;  // the RP_M-th smallest ord (exact)
+    // ---- compact everything at or below the pivot
+    if (t == 0) {
+        s_cnt = 0;
+        s_tie = 0x7fffffff;
+    }
+    for (int i = t; i < RP_M; i += RP_T) skey[i] = ~0ull;
+    __syncthreads();
+    for (long i = t; i < nlist; i += RP_T) {
+        uint32_t o = f2ord(row[i]);
+        if (metric == METRIC_IP) o = ~o;
+        if (o <= pivot) {
+            const int pos = atomicAdd(&s_cnt, 1);
+            if (pos < RP_M) skey[pos] = ((unsigned long long)o << 32) | (unsigned)i;
+        }
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    if (cnt > RP_M) {  // a long run of equal distances at the cut: leave the row to the full ranking
+        if (t == 0) {
+            sorted_upto[q] = 0;
+            tie0[q] = 0x7fffffff;
+        }
+        return;
+    }
+    unsigned long long e[RP_E];
+#pragma unroll
+    for (int r = 0; r < RP_E; r++) e[r] = skey[t * RP_E + r];
+    __syncthreads();
+    block_bitonic_sort<RP_E>(e, skey, RP_M, t, RP_T);
+    for (int i = t; i < cnt; i += RP_T) {
+        const unsigned long long key = skey[rr_sw(i)];
+        uint32_t o = (uint32_t)(key >> 32);
+        if (metric == METRIC_IP) o = ~o;
+        out_dis[q * nlist + i] = ord2f(o);
+        out_keys[q * nlist + i] = (int)(key & 0xffffffffu);
+        if (i + 1 < cnt && (uint32_t)(skey[rr_sw(i + 1)] >> 32) == (uint32_t)(key >> 32)) atomicMin(&s_tie, i);
+    }
+    __syncthreads();
+    if (t == 0) {
+        tie0[q] = s_tie;
+        sorted_upto[q] = cnt;
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -400,7 +530,8 @@ template <int METRIC>
 __global__ void __launch_bounds__(32)
 heap_order_kernel(const float* __restrict__ raw, long nlist, int k, const int* __restrict__ entry,
                   const int* __restrict__ fix_list, const int* __restrict__ nfix, float* __restrict__ out_dis,
-                  int* __restrict__ out_keys, int* __restrict__ tie0, const int* __restrict__ qbound) {
+                  int* __restrict__ out_keys, int* __restrict__ tie0, const int* __restrict__ qbound,
+                  int* __restrict__ sorted_upto) {
     if ((int)blockIdx.x >= *nfix) return;
     extern __shared__ __align__(16) unsigned long long hp[];  // hp[0] unused: 1-based heap, 16 B aligned pairs
     unsigned long long* h = hp;
@@ -604,7 +735,10 @@ heap_order_kernel(const float* __restrict__ raw, long nlist, int k, const int* _
         out_dis[q * nlist + i] = ord2f(o);
         out_keys[q * nlist + i] = (int)(uint32_t)(node & 0xffffffffu);
     }
-    if (lane == 0) tie0[q] = 0x7fffffff;
+    if (lane == 0) {
+        tie0[q] = 0x7fffffff;
+        if (sorted_upto && !straddle) sorted_upto[q] = k;  // the replay ranks the whole row
+    }
 }
 
 // entry[j], j < k: see heap_order_kernel.  Pure structure: simulate heap_pop on occupancy bits.
@@ -677,7 +811,7 @@ __global__ void collect_ties_kernel(const int* __restrict__ list, int n, const i
 
 void launch_fix_ties(int metric, const float* raw, long nlist, int k, const int* entry, const int* list, int n,
                      int* tie0, int bound, const int* qbound, int* fix_list, int* nfix, float* out_dis, int* out_keys,
-                     cudaStream_t s, const int* decided, int r0, int* err) {
+                     cudaStream_t s, const int* decided, int r0, int* err, int* sorted_upto) {
     if (n == 0) return;
     CUDA_CHECK(cudaMemsetAsync(nfix, 0, sizeof(int), s));
     collect_ties_kernel<<<(n + 255) / 256, 256, 0, s>>>(list, n, tie0, bound, qbound, decided, r0, k, nlist, out_dis,
@@ -686,12 +820,12 @@ void launch_fix_ties(int metric, const float* raw, long nlist, int k, const int*
     AUNCEL_CHECK(smem <= 220 * 1024, "nlist too large for the exact tie replay");
     auto kern = metric == METRIC_L2 ? heap_order_kernel<METRIC_L2> : heap_order_kernel<METRIC_IP>;
     if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<n, 32, smem, s>>>(raw, nlist, k, entry, fix_list, nfix, out_dis, out_keys, tie0, qbound);
+    kern<<<n, 32, smem, s>>>(raw, nlist, k, entry, fix_list, nfix, out_dis, out_keys, tie0, qbound, sorted_upto);
     CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_rank_rows(int metric, const float* dis, long nq, long nlist, float* out_dis, int* out_keys,
-                      int* tie0, cudaStream_t s) {
+                      int* tie0, cudaStream_t s, const int* qlist, int* sorted_upto, const int* qbound, int need_upto) {
     if (nq == 0) return;
     int P = 1;
     while (P < nlist) P <<= 1;
@@ -702,15 +836,27 @@ void launch_rank_rows(int metric, const float* dis, long nq, long nlist, float* 
         const int threads = P <= 8192 ? P / 8 : P / 16;
         AUNCEL_CHECK(threads <= 1024, "nlist too large for the in-smem centroid ranking");
         if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)nq, threads, smem, s>>>(metric, dis, nlist, P, out_dis, out_keys, tie0);
+        kern<<<(unsigned)nq, threads, smem, s>>>(metric, dis, nlist, P, out_dis, out_keys, tie0, qlist, sorted_upto, qbound,
+                                                 need_upto);
         CUDA_CHECK(cudaGetLastError());
         return;
     }
+    AUNCEL_CHECK(qlist == nullptr && sorted_upto == nullptr, "partial ranking needs nlist >= 256");
     if (smem > 48 * 1024)
         CUDA_CHECK(cudaFuncSetAttribute(rank_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int threads = std::max(32, std::min(1024, P / 2));
     rank_rows_kernel<<<(unsigned)nq, threads, smem, s>>>(metric, dis, nlist, P, out_dis, out_keys, tie0);
     CUDA_CHECK(cudaGetLastError());
 }
+
+// the RP_M best centroids per query (ties at the cut included); rows it cannot handle get sorted_upto = 0
+void launch_rank_rows_partial(int metric, const float* dis, long nq, long nlist, float* out_dis, int* out_keys,
+                              int* tie0, int* sorted_upto, cudaStream_t s) {
+    if (nq == 0) return;
+    rank_rows_partial_kernel<<<(unsigned)nq, RP_T, 0, s>>>(metric, dis, nlist, out_dis, out_keys, tie0, sorted_upto);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+int rank_rows_partial_width() { return RP_M; }
 
 }  // namespace auncel

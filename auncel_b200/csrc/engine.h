@@ -137,6 +137,9 @@ struct IvfIndex {
     DevBuf<float> c_dis;       // n x nlist coarse distances, ranked
     DevBuf<int> c_keys;        // n x nlist ranked centroid ids
     DevBuf<int> c_tie0;        // n: first rank with an equal-distance neighbour (INT_MAX: none / replayed)
+    DevBuf<int> c_sorted;      // n: ranks of the row that are in place (partial ranking), nlist = all
+    bool partial_rank = false; // last coarse_rank ranked only the best centroids
+    int partial_rank_mode = 1; // 0 never, 1 large batches, 2 whenever nlist allows (tests)
     DevBuf<int> fix_list;      // scratch for the tie replay
     DevBuf<int> heap_entry;    // heap_entry_table(heap_entry_k), device copy
     int heap_entry_k = -1;
@@ -211,7 +214,7 @@ struct IvfIndex {
                          const float* U, const float* sigma, float multipler, float std_m);
 
     // coarse: ranks all nlist centroids for n staged queries (x_dev n x d) into c_dis/c_keys
-    void coarse_rank(long n, const float* x_dev);
+    void coarse_rank(long n, const float* x_dev, bool allow_partial = false);
     void search(const QueryBatch& qb);
     // IndexIVF::range_search: lims_host gets n + 1 offsets; distances / labels stay in range_D / range_I
     void range_search(long n, const float* x_dev, float radius, int nprobe, long long* lims_host);
@@ -226,13 +229,17 @@ void launch_coarse_distances(int metric, const float* xq, long nq, const float* 
                              int dpad, float* out_dis /*nq x nlist or null*/,
                              unsigned long long* out_best /*nq or null*/, cudaStream_t s);
 void launch_rank_rows(int metric, const float* dis, long nq, long nlist, float* out_dis, int* out_keys,
-                      int* tie0, cudaStream_t s);
+                      int* tie0, cudaStream_t s, const int* qlist = nullptr, int* sorted_upto = nullptr,
+                      const int* qbound = nullptr, int need_upto = 0);
+void launch_rank_rows_partial(int metric, const float* dis, long nq, long nlist, float* out_dis, int* out_keys,
+                              int* tie0, int* sorted_upto, cudaStream_t s);
+int rank_rows_partial_width();
 // replay the reference's size-k heap for the queries of `list` (all n if null) that have equal
 // coarse distances below rank `bound`; rewrites their rows of out_dis/out_keys in heap order
 void heap_entry_table(int k, std::vector<int>& entry);
 void launch_fix_ties(int metric, const float* raw, long nlist, int k, const int* entry, const int* list, int n,
                      int* tie0, int bound, const int* qbound, int* fix_list, int* nfix, float* out_dis, int* out_keys, cudaStream_t s,
-                     const int* decided = nullptr, int r0 = 0, int* err = nullptr);
+                     const int* decided = nullptr, int r0 = 0, int* err = nullptr, int* sorted_upto = nullptr);
 void launch_interdis(int metric, const float* cent, long nlist, int dpad, float* out, cudaStream_t s);
 void launch_merge_tables(int metric, long n, long k, long nshard, const float* all_D,
                          const long long* all_I, const long long* translations, float* D,

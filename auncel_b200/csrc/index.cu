@@ -327,19 +327,32 @@ ErrModelView IvfIndex::model_view() const {
 }
 
 // IndexFlat::search with k = nlist (IndexFlat.cpp:42-56): all centroids, best first.
-void IvfIndex::coarse_rank(long n, const float* xs /* n x dpad, device */) {
+void IvfIndex::coarse_rank(long n, const float* xs /* n x dpad, device */, bool allow_partial) {
     c_dis.ensure((size_t)n * nlist);
     c_keys.ensure((size_t)n * nlist);
     c_tie0.ensure(n);
+    c_sorted.ensure(n);
     fix_list.ensure(n);
+    // Auncel mode ranks all nlist centroids per query but probes a few hundred: large batches rank the best
+    // rank_rows_partial_width() up front and complete a row only when a round is about to read past that
+    partial_rank = allow_partial && partial_rank_mode != 0 && nlist >= 4L * rank_rows_partial_width() &&
+                   (n >= 2048 || partial_rank_mode == 2);
     DevBuf<float>& raw = c_raw;  // kept for the whole search: the tie replay reads it
     const long chunk = 65535L * 64;
     raw.ensure((size_t)n * nlist);
     for (long i0 = 0; i0 < n; i0 += chunk) {
         long m = std::min(chunk, n - i0);
         launch_coarse_distances(metric, xs + i0 * dpad, m, centroids.p, nlist, dpad, raw.p + i0 * nlist, nullptr, stream);
-        launch_rank_rows(metric, raw.p + i0 * nlist, m, nlist, c_dis.p + i0 * nlist, c_keys.p + i0 * nlist,
-                         c_tie0.p + i0, stream);
+        if (partial_rank) {
+            launch_rank_rows_partial(metric, raw.p + i0 * nlist, m, nlist, c_dis.p + i0 * nlist, c_keys.p + i0 * nlist,
+                                     c_tie0.p + i0, c_sorted.p + i0, stream);
+            // rows the partial kernel gave up on (a long run of equal distances at the cut): sorted_upto == 0
+            launch_rank_rows(metric, raw.p + i0 * nlist, m, nlist, c_dis.p + i0 * nlist, c_keys.p + i0 * nlist,
+                             c_tie0.p + i0, stream, nullptr, c_sorted.p + i0, nullptr, 1);
+        } else {
+            launch_rank_rows(metric, raw.p + i0 * nlist, m, nlist, c_dis.p + i0 * nlist, c_keys.p + i0 * nlist,
+                             c_tie0.p + i0, stream);
+        }
     }
 }
 
@@ -379,7 +392,7 @@ void IvfIndex::search(const QueryBatch& qb) {
         launch_pad_rows(qb.x, n, d, q_x.p, dpad, stream);
         xs = q_x.p;
     }
-    coarse_rank(n, xs);
+    coarse_rank(n, xs, qb.mode != 0 && qb.max_codes == 0 && !qb.time_tune);
     if (tc_mode) launch_row_norms(xs, n, dpad, qnorm.ensure(n), stream);
     CUDA_CHECK(cudaEventRecord(ev2, stream));
     CUDA_CHECK(cudaMemsetAsync(ctl.p, 0, (CTL_SIZE + 8) * sizeof(int), stream));
@@ -438,11 +451,11 @@ void IvfIndex::search(const QueryBatch& qb) {
     // Small batches: one replay wave fits every tie-affected query, so fix all ranks up front
     // instead of paying one wave per round.  Large batches: only what set_online reads
     // (ranks 0..max_num) now, the rest lazily before each round.
-    const bool ties_all_upfront = exact_ties && n >= 16 && n <= 1024;
+    const bool ties_all_upfront = exact_ties && n >= 16 && n <= 1024 && !partial_rank;  // (a partial ranking only knows the ties of its prefix)
     if (exact_ties && (qb.mode != 0 || ties_all_upfront))
         launch_fix_ties(metric, c_raw.p, nlist, nprobe, entry_table(nprobe), nullptr, (int)n, c_tie0.p,
                         ties_all_upfront ? nprobe : tp.max_num + 1, nullptr, fix_list.p, ctl.p + CTL_NFIX, c_dis.p,
-                        c_keys.p, stream);
+                        c_keys.p, stream, nullptr, 0, nullptr, partial_rank ? c_sorted.p : nullptr);
     if (qb.mode != 0) {
         float* dtb_p = qb.dtb_out ? qb.dtb_out : dtb.ensure((size_t)n * tp.max_num);
         launch_set_online(metric, nlist, n, c_dis.p, c_keys.p, interdis.p, d_arcos.p, (int)h_arcos.size(), dtb_p,
@@ -549,7 +562,8 @@ void IvfIndex::search(const QueryBatch& qb) {
         // the K best (sort in shared memory, capacity 2 * KP) instead of an exact redo of the pair
         int KP = 16;
         while (KP < K) KP <<= 1;
-        const int cap = (use_tc && r0 < wide_slot_r0) ? std::max(K, 2 * KP) : K;
+        // (merge_check can order 2 KP entries itself -- the audit path --, slot_sort_kernel 512)
+        const int cap = (use_tc && r0 < wide_slot_r0) ? std::max(K, tc_audit ? 2 * KP : std::min(4 * KP, 512)) : K;
         rp.cap = cap;
         pool.ensure(slots * cap * 8);
         rp.cand_d = reinterpret_cast<float*>(pool.p);
@@ -567,6 +581,10 @@ void IvfIndex::search(const QueryBatch& qb) {
             scan_ev.push_back(a);
             scan_ev.push_back(b);
         }
+        if (partial_rank && r0 + (int)w + 1 > rank_rows_partial_width())
+            // this round reads ranks the partial ranking did not produce: complete the rows that need them
+            launch_rank_rows(metric, c_raw.p, n_active, nlist, c_dis.p, c_keys.p, c_tie0.p, stream, act_cur, c_sorted.p,
+                             rp.st.bound, r0 + (int)w + 1);
         if (exact_ties && !ties_all_upfront && !ties_done) {
             // ranks [r0, r0+w) are about to be scanned: their order must be the reference's.  Once
             // the remaining queries fit one replay wave, fix all of their ranks and stop checking.
@@ -574,7 +592,8 @@ void IvfIndex::search(const QueryBatch& qb) {
             const bool all_now = n_active <= 1000 && qb.mode != 1;
             launch_fix_ties(metric, c_raw.p, nlist, nprobe, entry_table(nprobe), act_cur, n_active, c_tie0.p,
                             all_now ? nprobe : r0 + (int)w, rp.st.bound, fix_list.p, ctl.p + CTL_NFIX, c_dis.p,
-                            c_keys.p, stream, qb.mode == 1 ? rp.st.decided : nullptr, r0, ctl.p + CTL_ERR);
+                            c_keys.p, stream, qb.mode == 1 ? rp.st.decided : nullptr, r0, ctl.p + CTL_ERR,
+                            partial_rank ? c_sorted.p : nullptr);
             ties_done = all_now;
         }
         CUDA_CHECK(cudaMemsetAsync(rp.round_work, 0, 4 * sizeof(unsigned long long), stream));

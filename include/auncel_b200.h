@@ -186,7 +186,8 @@ int auncel_index_get_round_stats(const AuncelIndex* idx, int max_rounds, double*
 
 /* engine switches (results never change): "tensor_core_filter" 0 off / 1 automatic / 2 whenever
  * every active query holds K results; "exact_ties" 0/1 replay of the reference's heap order for
- * equal centroid distances; "tc_audit" 0/1 (tests) redo every tensor-core round with the exact scan and
+ * equal centroid distances; "partial_rank" 0 / 1 / 2: rank only the best 1024 centroids of a query up front and
+ * complete a row when a round reads past them -- never / for batches >= 2048 (default) / always; "tc_audit" 0/1 (tests) redo every tensor-core round with the exact scan and
  * compare the candidate slots */
 int auncel_index_set_option(AuncelIndex* idx, const char* name, int value);
 

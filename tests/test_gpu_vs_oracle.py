@@ -195,6 +195,59 @@ def test_merge_tables_tie_order(metric, nshard, k):
     assert np.array_equal(I, I2)
 
 
+@pytest.mark.parametrize("metric", [O.L2, O.IP])
+def test_partial_centroid_ranking_nlist4096(metric):
+    """nlist = 4096 with the partial ranking forced on (option partial_rank = 2): only the best 1024
+    centroids are ranked up front, rows are completed when a round reads past them, ties are replayed as
+    before.  Distances, my_nprobe and labels against the restatement, which ranks everything like the
+    reference (IndexFlat::search with k = nlist)."""
+    d, nlist, nb, k, qk = 16, 4096, 150000, 20, 5
+    norm = metric == O.IP
+    xb = synth.clustered(3, nb, d, 600, 0.3, normalize=norm)
+    cent = synth.clustered(53, nlist, d, 600, 0.3, normalize=norm)
+    orc = O.OracleIndex(d, nlist, metric)
+    orc.set_centroids(cent)
+    orc.add(xb)
+    ix = ab.IndexIVFFlat(d, nlist, metric)
+    ix.set_centroids(cent)
+    ix.add(xb)
+    xq = synth.clustered(21, 400, d, 600, 0.3, normalize=norm)
+    if norm:
+        sizes = ix.list_sizes()
+        dis, keys = orc.coarse(xq, 1)
+        xq = xq[(sizes[keys[:, 0]] >= k) & (dis[:, 0] <= 1.0)]
+    xq = xq[:len(xq) // 20 * 20]
+    n = len(xq)
+    ts = n // 2
+    gD, gI = orc.search_fixed(xq, k, nlist)
+    orc.calibrate(xq[:ts], gD[:ts])
+    ix.set_option("partial_rank", 2)
+    es = ab.Error_sys(ix, n, k)
+    es.set_gt(gD, gI)
+    es.sys_train(ts, xq)
+    for a, b in zip(ix.traces(), orc.traces):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    for mult, stdm, eb in [(7.9, 6.0, 0.1), (40.0, 1.0, 0.05)]:  # the second one drives my_nprobe past 1024
+        acc = np.full(n, 1 - eb, np.float32)
+        es.set_topk(qk)
+        es.setparam(mult, stdm)
+        es.set_queries(n - ts, xq, acc, n)
+        D, I = es.search(ts)
+        orc.multipler, orc.std_m = mult, stdm
+        D2, I2, mynp, _ = orc.search_bounded(xq[ts:], k, qk, acc, gt_D=gD, offset=ts)
+        assert np.array_equal(es.my_nprobe[ts:], mynp[ts:]), (mult, stdm)
+        assert np.array_equal(D, D2)
+        assert_results_match(D, I, D2, I2, what=f"partial rank {mult}")
+        # the same through the full ranking
+        ix.set_option("partial_rank", 0)
+        es.set_queries(n - ts, xq, acc, n)
+        D3, I3 = es.search(ts)
+        ix.set_option("partial_rank", 2)
+        assert np.array_equal(D3, D) and np.array_equal(I3, I)
+    assert mynp[ts:].max() > 1024
+
+
 def test_shard_group_world_of_one():
     """auncel_shard_group_* with a single shard: no NCCL, the packed table goes straight to the merge."""
     from auncel_b200 import distributed as AD
