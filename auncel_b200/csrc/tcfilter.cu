@@ -38,6 +38,7 @@ constexpr int TC_ASTAGES = TC_ASTAGES_CFG;
 constexpr int TC_A_BYTES = 128 * 128;        // 128 rows x 32 f32
 constexpr int TC_B_MAX = TC_BKB_CFG * 1024;  // resident query tile: nchunk x N x 128 B
 constexpr int TC_NMAX = 256;
+constexpr int TC_RES = 256;  // survivor-list entries an epilogue warp reserves per global atomic
 constexpr size_t TC_SMEM = 1024 + TC_B_MAX + (size_t)TC_ASTAGES * TC_A_BYTES + 2 * (TC_NMAX * 8 + 64);
 
 struct TileMeta {
@@ -320,6 +321,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
         const int wq = warp & 3;  // TMEM lane quarter this warp may read
         const int grp = (warp - 2) >> 2;
         unsigned blkc = 0;
+        int res_pos = 0, res_end = 0;  // this warp's reserved range of the survivor list
         for (unsigned t = 0;; t++) {
             const int m = t & 1;
             MB_WAIT(8, &m_full[m], (t >> 1) & 1);
@@ -369,10 +371,21 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                             const int up = __shfl_up_sync(0xffffffffu, incl, o);
                             if (lane >= o) incl += up;
                         }
-                        int base = 0;
-                        if (lane == 31) base = atomicAdd(&rp.ctl[CTL_NCAND], incl);
-                        base = __shfl_sync(0xffffffffu, base, 31);
-                        int pos = base + incl - mine;
+                        // the warp owns a reserved range [res_pos, res_end) of the survivor list and refills it
+                        // RES entries at a time: one global atomic per ~RES survivors instead of one per chunk
+                        const int total = __shfl_sync(0xffffffffu, incl, 31);
+                        if (res_pos + total > res_end) {
+                            // hand the unused tail back as holes, then take a fresh range
+                            for (int t2 = res_pos + lane; t2 < res_end; t2 += 32)
+                                if ((unsigned)t2 < (unsigned)ta.cand_cap) ta.cand[t2] = ~0ull;
+                            const int want = max(total, TC_RES);
+                            int b2 = 0;
+                            if (lane == 0) b2 = atomicAdd(&rp.ctl[CTL_NCAND], want);
+                            res_pos = __shfl_sync(0xffffffffu, b2, 0);
+                            res_end = res_pos + want;
+                        }
+                        int pos = res_pos + incl - mine;
+                        res_pos += total;
                         while (hits) {
                             const int j = __ffs(hits) - 1;
                             hits &= hits - 1;
@@ -391,6 +404,8 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
             __syncwarp();
             if (lane == 0) mb_arrive(&m_empty[m]);
         }
+        for (int t2 = res_pos + lane; t2 < res_end; t2 += 32)  // unused tail of the last reservation: holes
+            if ((unsigned)t2 < (unsigned)ta.cand_cap) ta.cand[t2] = ~0ull;
     }
 #ifdef TC_TIMING
     if (blockIdx.x == 0 && lane == 0 && (warp <= 2 || warp == 6 || warp == 10)) {
@@ -411,6 +426,7 @@ __global__ void rerank_kernel(RoundParams rp, TcArgs ta) {
     const int ncand = (int)min((unsigned)rp.ctl[CTL_NCAND], (unsigned)ta.cand_cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += gridDim.x * blockDim.x) {
         const unsigned long long c = ta.cand[i];
+        if (c == ~0ull) continue;  // hole: unused part of a warp's reservation
         const int pos = (int)(c >> 32);
         const unsigned v = (unsigned)(c & 0xffffffffu);
         const unsigned long long pr = rp.pairs[pos];
