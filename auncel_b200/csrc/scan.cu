@@ -289,6 +289,44 @@ __device__ __forceinline__ float key_tau(unsigned k) {
     return ord2f(METRIC == METRIC_L2 ? k : ~k);
 }
 
+// 256 keys, 8 per lane (lane l owns positions 8l .. 8l+7), sorted ascending in registers: compare-exchange
+// distances below 8 never leave the lane, the others are one shuffle pair each -- no shared-memory round trip
+// and no warp barrier per network stage, which is what a lone warp waits for in warp_sort_smem.
+__device__ __forceinline__ void warp_sort_reg8(unsigned long long (&e)[8], int lane) {
+    const int base = lane * 8;
+#pragma unroll 1
+    for (int size = 2; size <= 256; size <<= 1) {
+        int stride = size >> 1;
+        for (; stride >= 8; stride >>= 1) {
+            const int lm = stride >> 3;
+            const bool keep_min = ((lane & lm) == 0) == ((base & size) == 0);
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const unsigned lo32 = __shfl_xor_sync(0xffffffffu, (unsigned)e[r], lm);
+                const unsigned hi32 = __shfl_xor_sync(0xffffffffu, (unsigned)(e[r] >> 32), lm);
+                const unsigned long long o = ((unsigned long long)hi32 << 32) | lo32;
+                e[r] = keep_min ? (o < e[r] ? o : e[r]) : (o > e[r] ? o : e[r]);
+            }
+        }
+#pragma unroll
+        for (int st = 4; st > 0; st >>= 1) {
+            if (st <= stride) {
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    if ((r & st) == 0) {
+                        const bool up = ((base + r) & size) == 0;
+                        const unsigned long long a = e[r], b = e[r | st];
+                        if ((a > b) == up) {
+                            e[r] = b;
+                            e[r | st] = a;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // sort the buffer, keep the K best, tighten tau when K are held
 template <int METRIC>
 __device__ __forceinline__ void compact(unsigned long long* buf, int& cnt, float& tau, int K, int lane) {
@@ -296,14 +334,16 @@ __device__ __forceinline__ void compact(unsigned long long* buf, int& cnt, float
         for (int i = cnt + lane; i < 64; i += 32) buf[i] = ~0ull;
         __syncwarp();
         warp_sort_smem<64>(buf, lane);
-    } else if (cnt <= 128) {
-        for (int i = cnt + lane; i < 128; i += 32) buf[i] = ~0ull;
-        __syncwarp();
-        warp_sort_smem<128>(buf, lane);
     } else {
-        for (int i = cnt + lane; i < CAP; i += 32) buf[i] = ~0ull;
+        static_assert(CAP == 256, "warp_sort_reg8 sorts exactly 256 keys");
+        unsigned long long e[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) e[r] = lane * 8 + r < cnt ? buf[lane * 8 + r] : ~0ull;
+        warp_sort_reg8(e, lane);
         __syncwarp();
-        warp_sort_smem<CAP>(buf, lane);
+#pragma unroll
+        for (int r = 0; r < 8; r += 2)
+            *reinterpret_cast<ulonglong2*>(&buf[lane * 8 + r]) = make_ulonglong2(e[r], e[r + 1]);
     }
     if (cnt > K) cnt = K;
     if (cnt == K) tau = key_dist<METRIC>(buf[K - 1]);
