@@ -304,6 +304,145 @@ void launch_slot_sort(const RoundParams& rp, int num_sms, cudaStream_t s) {
     CUDA_CHECK(cudaGetLastError());
 }
 
+// --------------------------------------------------------------------------- warp-level networks in registers
+// 32 E keys, E per lane (lane l owns positions E l .. E l + E - 1).  Compare-exchange distances below E stay in
+// the lane, the others are a shuffle pair: a lone warp pays no shared-memory round trip and no barrier per stage.
+template <int E>
+__device__ __forceinline__ void warp_merge_reg(unsigned long long (&e)[E], int lane) {  // bitonic input -> ascending
+#pragma unroll
+    for (int lm = 16; lm > 0; lm >>= 1) {
+        const bool keep_min = (lane & lm) == 0;
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+            const unsigned lo32 = __shfl_xor_sync(0xffffffffu, (unsigned)e[r], lm);
+            const unsigned hi32 = __shfl_xor_sync(0xffffffffu, (unsigned)(e[r] >> 32), lm);
+            const unsigned long long o = ((unsigned long long)hi32 << 32) | lo32;
+            e[r] = keep_min ? (o < e[r] ? o : e[r]) : (o > e[r] ? o : e[r]);
+        }
+    }
+#pragma unroll
+    for (int st = E / 2; st > 0; st >>= 1)
+#pragma unroll
+        for (int r = 0; r < E; r++)
+            if ((r & st) == 0) {
+                const unsigned long long a = e[r], b = e[r | st];
+                if (a > b) {
+                    e[r] = b;
+                    e[r | st] = a;
+                }
+            }
+}
+
+template <int E>
+__device__ __forceinline__ void warp_sort_reg(unsigned long long (&e)[E], int lane) {  // any input -> ascending
+    const int base = lane * E;
+#pragma unroll 1
+    for (int size = 2; size <= 32 * E; size <<= 1) {
+        int stride = size >> 1;
+        for (; stride >= E; stride >>= 1) {
+            const int lm = stride / E;
+            const bool keep_min = ((lane & lm) == 0) == ((base & size) == 0);
+#pragma unroll
+            for (int r = 0; r < E; r++) {
+                const unsigned lo32 = __shfl_xor_sync(0xffffffffu, (unsigned)e[r], lm);
+                const unsigned hi32 = __shfl_xor_sync(0xffffffffu, (unsigned)(e[r] >> 32), lm);
+                const unsigned long long o = ((unsigned long long)hi32 << 32) | lo32;
+                e[r] = keep_min ? (o < e[r] ? o : e[r]) : (o > e[r] ? o : e[r]);
+            }
+        }
+#pragma unroll
+        for (int st = E / 2; st > 0; st >>= 1) {
+            if (st <= stride) {
+#pragma unroll
+                for (int r = 0; r < E; r++) {
+                    if ((r & st) == 0) {
+                        const bool up = ((base + r) & size) == 0;
+                        const unsigned long long a = e[r], b = e[r | st];
+                        if ((a > b) == up) {
+                            e[r] = b;
+                            e[r | st] = a;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// the 2 KP keys of a merge (ascending held results ++ descending candidates) -> ascending, through registers
+template <int KP>
+__device__ __forceinline__ void merge_keys(unsigned long long* key, int lane) {
+    constexpr int E = 2 * KP / 32;
+    unsigned long long e[E];
+#pragma unroll
+    for (int r = 0; r < E; r++) e[r] = key[lane * E + r];
+    warp_merge_reg<E>(e, lane);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < E; r++) key[lane * E + r] = e[r];
+    __syncwarp();
+}
+
+// error_pro::cur_num (IVF_pro.cpp:258-291) evaluated by a whole warp.  The reference probes U(phi(D[j])) for
+// j = query_k - 1 and then along a binary search; every probe is 15 arccos-LUT terms summed in order
+// (sum_angle, :162-177) plus a bucket search (Trace::search, :84-107) -- scalar work that would otherwise run
+// once per probe on a full warp.  Here lane j computes U for rank j (all ranks at once, same arithmetic and
+// summation order per rank), then the reference's decisions are replayed on the precomputed values.  Error
+// bits are taken only from the ranks the reference would have probed.
+__device__ __forceinline__ unsigned cur_num_warp(const ErrModelView& m, const float* D, const float* dtb, int index,
+                                                 unsigned query_k, int* err, int lane) {
+    const int start = (1 << index) - 1;
+    float u[4];    // ranks lane, lane + 32, ... (query_k <= MAX_K = 128)
+    int e_l[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        u[b] = 0.f;
+        e_l[b] = 0;
+        const unsigned j = b * 32 + lane;
+        if (b * 32 < (int)query_k) {
+            if (j < query_k) u[b] = model_U(m, index, sum_angle(D[j], dtb, 15, start, m.arcos, m.arcos_size, &e_l[b]));
+        }
+    }
+    int used_err = 0;
+    auto probe = [&](long j) -> float {  // value and error bits of rank j, as if computed now
+        float v = 0.f;
+        int e = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if ((j >> 5) == b) {
+                v = __shfl_sync(0xffffffffu, u[b], (int)(j & 31));
+                e = __shfl_sync(0xffffffffu, e_l[b], (int)(j & 31));
+            }
+        used_err |= e;
+        return v;
+    };
+    long high = (long)query_k - 1, low = 0;
+    unsigned result;
+    {
+        const float uh = probe(high);
+        // size_t*float -> float; size_t*1.005 -> double
+        if ((double)fmul((float)query_k, uh) <= dmul((double)query_k, 1.005)) {
+            *err |= used_err;
+            return query_k;
+        }
+    }
+    result = 0xffffffffu;
+    while (low <= high) {
+        const long middle = (low + high) / 2;
+        if (middle <= 0) {
+            result = 0;
+            break;
+        }
+        const float um = probe(middle);
+        if (fmul((float)(middle + 1), um) <= (float)query_k)
+            low = middle + 1;
+        else
+            high = middle - 1;
+    }
+    *err |= used_err;
+    return result == 0xffffffffu ? (unsigned)(low + 1) : result;
+}
+
 // --------------------------------------------------------------------------- merge + check
 constexpr int MC_WARPS = 4;
 constexpr int MC_INSERT_MAX = 8;  // slots with at most this many candidates are merged by insertion
@@ -377,19 +516,31 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
                 // over the whole upper half (pads = largest first), the lower half gets the held results
                 for (int i = KP + T + lane; i < 2 * KP; i += 32) sm.key[i] = ~0ull;
                 __syncwarp();
-                for (int size = 2; size <= KP; size <<= 1)
-                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                        for (int t = lane; t < KP / 2; t += 32) {
-                            const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-                            const bool down = ((lo & size) == 0);  // descending overall
-                            const unsigned long long x = sm.key[KP + lo], y = sm.key[KP + hi];
-                            if ((x < y) == down) {
-                                sm.key[KP + lo] = y;
-                                sm.key[KP + hi] = x;
+                if (KP >= 32) {
+                    constexpr int E2 = KP >= 32 ? KP / 32 : 1;
+                    unsigned long long e2[E2];
+#pragma unroll
+                    for (int r = 0; r < E2; r++) e2[r] = sm.key[KP + lane * E2 + r];
+                    warp_sort_reg<E2>(e2, lane);
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < E2; r++) sm.key[2 * KP - 1 - (lane * E2 + r)] = e2[r];  // descending
+                    __syncwarp();
+                } else {
+                    for (int size = 2; size <= KP; size <<= 1)
+                        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                            for (int t = lane; t < KP / 2; t += 32) {
+                                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                                const bool down = ((lo & size) == 0);  // descending overall
+                                const unsigned long long x = sm.key[KP + lo], y = sm.key[KP + hi];
+                                if ((x < y) == down) {
+                                    sm.key[KP + lo] = y;
+                                    sm.key[KP + hi] = x;
+                                }
                             }
+                            __syncwarp();
                         }
-                        __syncwarp();
-                    }
+                }
                 for (int i = lane; i < KP; i += 32) {
                     unsigned long long k1 = ~0ull;
                     if (i < rcnt) {
@@ -400,18 +551,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
                     sm.key[i] = k1;
                 }
                 __syncwarp();
-#pragma unroll 1
-                for (int stride = KP; stride > 0; stride >>= 1) {
-                    for (int t = lane; t < KP; t += 32) {
-                        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-                        const unsigned long long x = sm.key[lo], y = sm.key[hi];
-                        if (x > y) {
-                            sm.key[lo] = y;
-                            sm.key[hi] = x;
-                        }
-                    }
-                    __syncwarp();
-                }
+                merge_keys<KP>(sm.key, lane);
                 rcnt = min(K, rcnt + T);
                 for (int i = lane; i < KP; i += 32) {
                     if (i < rcnt) {
@@ -656,19 +796,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
                 sm.key[2 * KP - 1 - i] = k2;
             }
             __syncwarp();
-#pragma unroll 1
-            for (int stride = KP; stride > 0; stride >>= 1) {
-                for (int t = lane; t < KP; t += 32) {
-                    int lo = 2 * t - (t & (stride - 1));
-                    int hi = lo + stride;
-                    unsigned long long x = sm.key[lo], y = sm.key[hi];
-                    if (x > y) {
-                        sm.key[lo] = y;
-                        sm.key[hi] = x;
-                    }
-                }
-                __syncwarp();
-            }
+            merge_keys<KP>(sm.key, lane);
             rcnt = min(K, rcnt + c);
             for (int i = lane; i < KP; i += 32) {
                 if (i < rcnt) {
@@ -709,7 +837,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
                         __syncwarp();
                         S = sm.ang;
                     }
-                    pre = cur_num(tp.model, S, dtb, ind, qk, &err);
+                    pre = cur_num_warp(tp.model, S, dtb, ind, qk, &err, lane);
                     cached_pre = pre;
                     cached_ind = ind;
                     topq_dirty = 0;
