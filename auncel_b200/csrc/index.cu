@@ -525,7 +525,9 @@ void IvfIndex::search(const QueryBatch& qb) {
         if (n_active <= 64) nsub = 1;
         while (nsub > 1 && (size_t)n_active * w * nsub * K > pool_entries) nsub >>= 1;
         while (S > 1 && (size_t)n_active * w * S * nsub * K > pool_entries) S--;
-        rp.qt = SCAN_QT / nsub;
+        static const int nc4 = getenv("AUNCEL_NC4") ? atoi(getenv("AUNCEL_NC4")) : 1;
+        rp.nc = (nsub == 4 && nc4) ? 4 : 8;
+        rp.qt = 4 * rp.nc / nsub;
         rp.nsub = nsub;
         rp.unsorted = 0;
         rp.merged = 0;
@@ -673,7 +675,8 @@ void IvfIndex::search(const QueryBatch& qb) {
                     redo_pool.ensure(nredo * 4 * K * 8);
                     RoundParams rr = rp;
                     rr.filtered = 1;
-                    rr.qt = SCAN_QT / 4;  // narrow tiles: 8 queries, the 128 rows of a block split over 4 warps
+                    rr.nc = nc4 ? 4 : 8;
+                    rr.qt = rr.nc;  // narrow tiles: 4 * nc / nsub queries, the 128 rows of a block split over 4 warps
                     rr.nsub = 4;
                     rr.S = 1;
                     rr.cap = K;

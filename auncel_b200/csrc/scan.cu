@@ -145,16 +145,14 @@ void launch_plan(const RoundParams& rp, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------- scan
-constexpr int NCONS = 8;                          // consumer warps
-constexpr int THREADS = (NCONS + 1) * 32;         // + 1 producer warp
-constexpr int STAGES = 6;
+constexpr int MAX_STAGES = 6;
 constexpr int QLD = SCAN_DK;                      // query row in smem, floats (dense TMA box)
 constexpr int VT_BYTES = SCAN_VT * SCAN_DK * 4;   // 16384: 128 rows x 128 B, 128B-swizzled by TMA
 constexpr int QT_BYTES = SCAN_QT * QLD * 4;       // 4096
 constexpr int HDR_BYTES = 512;
 constexpr int STAGE_BYTES = VT_BYTES + QT_BYTES + HDR_BYTES + 512;  // 21504 = 21 * 1024
 constexpr int CAP = 256;                          // candidate buffer per query (>= MAX_K + 32)
-constexpr size_t SCAN_SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)SCAN_QT * CAP * 8;
+constexpr size_t scan_smem(int nc) { return 1024 + (size_t)(nc == 8 ? 6 : 3) * STAGE_BYTES + (size_t)nc * 4 * CAP * 8; }
 static_assert(STAGE_BYTES % 1024 == 0, "stages must keep the 1024 B alignment SWIZZLE_128B needs");
 
 struct StageHdr {
@@ -355,8 +353,13 @@ __device__ __forceinline__ void compact(unsigned long long* buf, int& cnt, float
 // RSPLIT = 4: 8 queries/tile; warp w owns queries 4(w/4)..+3 and 32 rows (1 per lane).
 // Splitting the rows keeps all warps busy when a list is probed by few queries; the RSPLIT row
 // subsets of a query are written as RSPLIT sub-slots.
-template <int METRIC, int RSPLIT>
-__global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap qmap) {
+// NC = consumer warps: 8 (one CTA per SM, 6 stages) or 4 (two CTAs per SM, 3 stages each).  With few queries
+// per list a tile is a latency-bound chain of stages; two independent chains per SM nearly double the rate.
+template <int METRIC, int RSPLIT, int NC>
+__global__ void __launch_bounds__((NC + 1) * 32, NC == 8 ? 1 : 2)
+scan_kernel(RoundParams rp, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap qmap) {
+    constexpr int NCONS = NC;
+    constexpr int STAGES = NC == 8 ? 6 : 3;
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES];
     // thresholds shared by the RSPLIT warps that scan different rows for the same query: a warp
@@ -471,7 +474,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(RoundParams rp, const 
 
     // =========================== consumers ===========================
     constexpr int TV = 4 / RSPLIT;                       // list rows per lane
-    constexpr int NGROUP = 8 / RSPLIT;                   // warps that share a row subset split the tile's queries
+    constexpr int NGROUP = NC / RSPLIT;                  // warps that share a row subset split the tile's queries
     const int group = warp / RSPLIT;
     const int rbase = (warp % RSPLIT) * (SCAN_VT / RSPLIT);  // first row of this warp (rows rbase + lane + 32 j)
     int cnt[4] = {0, 0, 0, 0};
@@ -669,13 +672,18 @@ void make_queries_tensor_map_tc(void* out_map, const float* xq_sorted, long long
 
 void launch_scan(const RoundParams& rp, const void* tmap, const void* qmap, int num_sms, cudaStream_t s) {
     void (*kern)(RoundParams, const CUtensorMap, const CUtensorMap);
+    const int nc = rp.nsub == 4 && rp.nc == 4 ? 4 : 8;
     if (rp.metric == METRIC_L2)
-        kern = rp.nsub == 4 ? scan_kernel<METRIC_L2, 4> : rp.nsub == 2 ? scan_kernel<METRIC_L2, 2> : scan_kernel<METRIC_L2, 1>;
+        kern = rp.nsub == 4 ? (nc == 4 ? scan_kernel<METRIC_L2, 4, 4> : scan_kernel<METRIC_L2, 4, 8>)
+                            : rp.nsub == 2 ? scan_kernel<METRIC_L2, 2, 8> : scan_kernel<METRIC_L2, 1, 8>;
     else
-        kern = rp.nsub == 4 ? scan_kernel<METRIC_IP, 4> : rp.nsub == 2 ? scan_kernel<METRIC_IP, 2> : scan_kernel<METRIC_IP, 1>;
-    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
-    kern<<<num_sms, THREADS, SCAN_SMEM, s>>>(rp, *reinterpret_cast<const CUtensorMap*>(tmap),
-                                            *reinterpret_cast<const CUtensorMap*>(qmap));
+        kern = rp.nsub == 4 ? (nc == 4 ? scan_kernel<METRIC_IP, 4, 4> : scan_kernel<METRIC_IP, 4, 8>)
+                            : rp.nsub == 2 ? scan_kernel<METRIC_IP, 2, 8> : scan_kernel<METRIC_IP, 1, 8>;
+    AUNCEL_CHECK(rp.qt == 4 * nc / rp.nsub || rp.nsub == 1, "scan tile shape and queries per tile disagree");
+    const size_t smem = scan_smem(nc);
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<num_sms * (nc == 4 ? 2 : 1), (nc + 1) * 32, smem, s>>>(rp, *reinterpret_cast<const CUtensorMap*>(tmap),
+                                                                 *reinterpret_cast<const CUtensorMap*>(qmap));
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -67,6 +67,7 @@ struct RoundParams {
     int r0, w, S;
     int qt;               // queries per scan tile this round: 32 / nsub
     int nsub;             // sub-slots per (query, rank, segment) = row subsets of the scan tile (1, 2 or 4)
+    int nc;               // consumer warps of the scan CTA: 8, or 4 (two CTAs per SM; narrow tiles only)
     int defer_sort;       // 1: the exact scan may hand over <= K candidates unsorted (many queries: merge_check has the warps)
     int merged;           // 1: stage_merge_kernel reduced every pair's S * nsub sub-slots to its first one
     int unsorted;         // (logging)  1: slots were filled by rerank_kernel in arrival order (tensor-core rounds)

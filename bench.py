@@ -577,7 +577,7 @@ SETUP_NOTE = ("setup (synthetic data, k-means, list assignment, ground truth, ca
               "the timed region is the unmodified reference alone")
 
 
-def cpu_sample_search(a, S, R, O, nsample, threads):
+def cpu_sample_search(a, S, R, O, nsample, threads, chunk=4):
     """Error_sys::search of the reference over `nsample` test queries on `threads` host threads."""
     ix = S["ix"]
     ncal = 10  # Error_sys needs a trained error_pro; its traces are then replaced by the full
@@ -591,7 +591,7 @@ def cpu_sample_search(a, S, R, O, nsample, threads):
     acc = np.full(ncal + nsample, 1.0 - a.eb, np.float32)
     R.set_queries(QUERY_TOPK, nsample, q, acc, *HYPER[a.eb])
     t0 = time.perf_counter()
-    D, I = R.es_search(ncal, nsample, threads=threads, chunk=4)  # dynamic hand-out, 4 queries at a time
+    D, I = R.es_search(ncal, nsample, threads=threads, chunk=chunk)  # dynamic hand-out, `chunk` queries at a time
     dt = time.perf_counter() - t0
     return dt, D, R.my_nprobe(ncal, nsample)
 

@@ -33,7 +33,9 @@ for name, thr in (("exact_coarse", 1 << 30), ("blas_coarse_default", 20)):
     O.RefIndex.set_blas_threshold(thr)
     R.clear_my_nprobe() if name != "exact_coarse" else None
     t0 = time.time()
-    dt, Dr, npr = B.cpu_sample_search(a, S, R, O, n, cores)
+    # 64 queries per IndexIVF::search call: above distance_compute_blas_threshold (20), so with the default
+    # threshold the coarse quantizer really takes the sgemm_ path (utils.cpp:644-655)
+    dt, Dr, npr = B.cpu_sample_search(a, S, R, O, n, cores, chunk=64)
     npr = npr.astype(np.int64)
     rec_r = W.recall_at(gt, Dr, 10, 1)
     rec_g = W.recall_at(gt, Dg, 10, 1)
