@@ -392,7 +392,8 @@ void IvfIndex::search(const QueryBatch& qb) {
         launch_pad_rows(qb.x, n, d, q_x.p, dpad, stream);
         xs = q_x.p;
     }
-    coarse_rank(n, xs, qb.mode != 0 && qb.max_codes == 0 && !qb.time_tune);
+    // (a plain search reads only its nprobe best centroids: the partial ranking covers them)
+    coarse_rank(n, xs, qb.max_codes == 0 && !qb.time_tune && (qb.mode != 0 || nprobe + 1 < rank_rows_partial_width()));
     if (tc_mode) launch_row_norms(xs, n, dpad, qnorm.ensure(n), stream);
     CUDA_CHECK(cudaEventRecord(ev2, stream));
     CUDA_CHECK(cudaMemsetAsync(ctl.p, 0, (CTL_SIZE + 8) * sizeof(int), stream));
@@ -505,6 +506,11 @@ void IvfIndex::search(const QueryBatch& qb) {
             static const long w1_env = getenv("AUNCEL_W1") ? atol(getenv("AUNCEL_W1")) : -1;
             const long w1 = w1_env >= 0 ? w1_env : 31;
             if (w1 > 0 && stats.rounds == 1 && n >= 2048 && tc_mode == 1) w = std::min<long>(max_stage - r0, std::max<long>(w, w1));
+        } else if (qb.mode == 0 && n >= 2048 && tc_mode == 1 && max_stage > 8) {
+            // plain search, large batch: the first list exactly (it fills the heaps), then the tensor-core
+            // filter -- one round of 31 ranks with wide slots, then everything that is left (every query scans
+            // all nprobe lists anyway; a filter round costs one pass over the lists whatever its width)
+            w = stats.rounds == 0 ? 1 : stats.rounds == 1 ? std::min<long>(w, 31) : w;
         } else if ((long)n_active * max_stage >= 4096 && max_stage > 8) {
             // plain / calibration search: a few narrow rounds first, so that the bulk of the
             // lists is scanned against a tight threshold (cheap selection)
