@@ -248,6 +248,57 @@ def test_partial_centroid_ranking_nlist4096(metric):
     assert mynp[ts:].max() > 1024
 
 
+def test_tie_exactly_at_the_stop_stage():
+    """Equal centroid distances that matter only because a query's stop stage falls between them.
+    767 distinct centroids around the queries, then 128 far-away PAIRS of identical centroids (ranks
+    767/768, 769/770, ...): with multipler = 900 a query that is satisfied after its first list stops at
+    stage 900, i.e. between the twins at ranks 899 and 900 -- which of the two (the one that holds the
+    vectors or its empty duplicate) is scanned is decided by the reference's heap order alone.  No query has
+    a tie below rank nlist/8 + 21, so nothing is replayed up front: this is the lazy stop-stage replay of
+    coarse.cu (collect_ties_kernel / heap_order_kernel, straddle mode)."""
+    d, nlist, k, qk = 8, 1024, 16, 4
+    rng = np.random.default_rng(17)
+    near = rng.standard_normal((767, d)).astype(np.float32)
+    far = (rng.standard_normal((128, d)) * 3.0 + 60.0).astype(np.float32)
+    cent = np.concatenate([near, np.repeat(far, 2, axis=0), (far[:1] + 500.0)]).astype(np.float32)
+    assert cent.shape == (nlist, d)
+    xb = np.concatenate([rng.standard_normal((6, d)).astype(np.float32),
+                         (np.repeat(far, 40, axis=0) + 0.05 * rng.standard_normal((5120, d))).astype(np.float32)])
+    xq = rng.standard_normal((1400, d)).astype(np.float32) * 0.5
+    orc = O.OracleIndex(d, nlist, O.L2)
+    orc.set_centroids(cent)
+    orc.add(xb)
+    ix = ab.IndexIVFFlat(d, nlist, O.L2)
+    ix.set_centroids(cent)
+    ix.add(xb)
+    cd, ck = orc.coarse(xq, nlist)
+    assert (cd[:, 1:767] == cd[:, :766]).any(1).mean() < 0.1, "(nearly) no ties among the near centroids"
+    assert (cd[:, 768::2][:, :64] == cd[:, 767::2][:, :64]).all(), "twins are equidistant"
+    gD, gI = orc.search_fixed(xq, k, nlist)
+    orc.calibrate(xq[:200], gD[:200])
+    es = ab.Error_sys(ix, 1400, k)
+    es.set_gt(gD, gI)
+    es.sys_train(200, xq)
+    for mult in (900.0, 901.0, 902.0):  # stop stage between twins / between two pairs / between twins
+        acc = np.full(1400, 0.5, np.float32)
+        es.set_topk(qk)
+        es.setparam(mult, 1.0)
+        es.set_queries(1200, xq, acc, 1400)
+        D, I = es.search(200)
+        st = ix.stats()
+        orc.multipler, orc.std_m = mult, 1.0
+        D2, I2, mynp, _ = orc.search_bounded(xq[200:], k, qk, acc, gt_D=gD, offset=200)
+        b = mynp[200:].astype(np.int64)
+        inside = (b > 767) & (b < nlist)
+        straddle = inside & (cd[200:][np.arange(1200), np.minimum(b, nlist - 1)] == cd[200:][np.arange(1200), np.minimum(b, nlist - 1) - 1])
+        assert (straddle.sum() > 1000) == (mult != 901.0), "the construction puts stop stages between twins"
+        assert np.array_equal(es.my_nprobe[200:], mynp[200:])
+        assert st["err_bits"] == 0
+        assert st["ndis"] == orc.last_stats["ndis"] and st["nlist"] == orc.last_stats["nlist"], "which twin was scanned"
+        assert np.array_equal(D, D2)
+        assert_results_match(D, I, D2, I2, what=f"stop-stage ties, multipler {mult}")
+
+
 def test_shard_group_world_of_one():
     """auncel_shard_group_* with a single shard: no NCCL, the packed table goes straight to the merge."""
     from auncel_b200 import distributed as AD
