@@ -71,6 +71,8 @@ SYMBOLS = {
     "auncel_shard_group_search_device": (C.c_int, [_h, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                                    C.c_void_p, C.c_void_p]),
     "auncel_shard_group_get_stats": (C.c_int, [_h, _d]),
+    "auncel_shard_group_set_bounded": (C.c_int, [_h, C.c_int]),
+    "auncel_shard_group_get_exchange_stats": (C.c_int, [_h, _d]),
     "auncel_index_copy_subset_to": (C.c_int, [_h, _h, C.c_int, C.c_int64, C.c_int64]),
 }
 

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <array>
+#include <functional>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -102,6 +103,24 @@ struct QueryBatch {
     long long* I = nullptr;   // n x k
     float* snapshots = nullptr;  // training: n x n_traces x k sorted distances
     float* dtb_out = nullptr;    // optional n x max_num (training needs it on the host)
+};
+
+struct RoundParams;
+
+// Candidate exchange between the shards of one index (shard_rounds.cu).  The collectives are injected by
+// the owner of the communicator (shards.cu: NCCL), the engine itself links no communication library.
+struct ShardExchange {
+    int rank = 0, world = 1;
+    // every rank contributes `bytes` bytes from `send`; `recv` receives world x bytes, in rank order
+    std::function<void(const void* send, void* recv, size_t bytes, cudaStream_t s)> all_gather;
+    // element-wise maximum over ranks, in place
+    std::function<void(long long* buf, size_t count, cudaStream_t s)> all_reduce_max;
+    DevBuf<unsigned long long> ctr;
+    DevBuf<int> cnt2, ovf_ord, fill, inv;
+    DevBuf<unsigned char> pool, send, recv, ovf_pool;
+    std::vector<unsigned long long> h_counts;
+    // since the last reset (one search): candidates this rank sent / all ranks sent, bytes received, rounds
+    uint64_t entries_sent = 0, entries_recv = 0, bytes_recv = 0, exchanges = 0;
 };
 
 struct IvfIndex {
@@ -216,6 +235,10 @@ struct IvfIndex {
     // coarse: ranks all nlist centroids for n staged queries (x_dev n x d) into c_dis/c_keys
     void coarse_rank(long n, const float* x_dev, bool allow_partial = false);
     void search(const QueryBatch& qb);
+    // error-bounded / calibration search over the shards of one index with single-index semantics: when
+    // set, every round of search() exchanges its candidates with the other ranks (shard_rounds.cu)
+    ShardExchange* shard_x = nullptr;
+    void exchange_candidates(RoundParams& rp, size_t nredo);
     // IndexIVF::range_search: lims_host gets n + 1 offsets; distances / labels stay in range_D / range_I
     void range_search(long n, const float* x_dev, float radius, int nprobe, long long* lims_host);
     int max_num() const { return (int)(nlist / 8 + 20); }

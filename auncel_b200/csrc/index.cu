@@ -416,6 +416,20 @@ void IvfIndex::search(const QueryBatch& qb) {
     rp.K = K;
     rp.st.carve(state.p, n, K);
     rp.ctl = ctl.p;
+    // shards with single-index semantics: error-bounded and calibration searches only (a plain search
+    // merges result tables instead, IndexShards.cpp:44-105)
+    const bool sharded = shard_x != nullptr && shard_x->world > 1 && qb.mode != 0;
+    rp.shard_rank = sharded ? shard_x->rank : -1;
+    if (sharded) {
+        AUNCEL_CHECK(qb.max_codes == 0 && !qb.time_tune, "sharded rounds: max_codes / time_tune cut on the local list sizes");
+        AUNCEL_CHECK(h_list_off[nlist] > 0, "sharded rounds: empty shard");
+        AUNCEL_CHECK(!tc_audit, "sharded rounds: tc_audit is a single-GPU check");
+        long long longest = 0;
+        for (long l = 0; l < nlist; l++) longest = std::max(longest, h_list_off[l + 1] - h_list_off[l]);
+        AUNCEL_CHECK(longest < (1ll << SHARD_CODE_SHIFT) && shard_x->world <= (1 << (32 - SHARD_CODE_SHIFT)),
+                     "sharded rounds: list too long / too many shards for the 32-bit candidate code");
+        shard_x->entries_sent = shard_x->entries_recv = shard_x->bytes_recv = shard_x->exchanges = 0;
+    }
     rp.round_work = round_work.ensure(4);
     h_round_work.ensure(4);
     std::vector<uint64_t> round_uniq, round_staged;
@@ -537,7 +551,7 @@ void IvfIndex::search(const QueryBatch& qb) {
         rp.nsub = nsub;
         rp.unsorted = 0;
         rp.merged = 0;
-        rp.defer_sort = n_active >= 1024 ? 1 : 0;  // few queries: one merge warp per query would sort serially
+        rp.defer_sort = (n_active >= 1024 && !sharded) ? 1 : 0;  // few queries: one merge warp per query would sort serially
         rp.filtered = 0;
         rp.pair_flag = nullptr;
         rp.redo_ord = nullptr;
@@ -610,6 +624,7 @@ void IvfIndex::search(const QueryBatch& qb) {
         CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds], stream));
         bool scanned = false;
         int tc_idx = -1;
+        size_t nredo_round = 0;
         if (use_tc) {
             TcArgs ta;
             ta.vnorm = vnorm.p;
@@ -698,6 +713,7 @@ void IvfIndex::search(const QueryBatch& qb) {
                     rp.redo_d = rr.cand_d;
                     rp.redo_off = rr.cand_off;
                     rp.redo_cnt = rr.slot_cnt;
+                    nredo_round = nredo;
                     launches += 5;
                 }
             }
@@ -712,6 +728,7 @@ void IvfIndex::search(const QueryBatch& qb) {
             }
         }
         CUDA_CHECK(cudaEventRecord(scan_ev[2 * stats.rounds + 1], stream));
+        if (sharded) exchange_candidates(rp, nredo_round);  // rp now describes the union of all shards' candidates
         launch_merge_check(rp, tp, stream);
         launches += 7 + (exact_ties && !ties_all_upfront ? 2 : 0);  // [collect_ties, heap_order,] plan x3, gather, scan, merge_check, compact_active
         launch_compact_active(rp, r0 + (int)w, act_nxt, h_ctl.p, stream);
@@ -739,6 +756,7 @@ void IvfIndex::search(const QueryBatch& qb) {
     st_dev.ensure(4);
     CUDA_CHECK(cudaMemsetAsync(st_dev.p, 0, 4 * sizeof(unsigned long long), stream));
     launch_finalize(rp, tp, qb.D, qb.I, qb.my_nprobe, st_dev.p, stream);
+    if (sharded) shard_x->all_reduce_max(qb.I, (size_t)n * K, stream);  // every label from the shard that holds the vector
     unsigned long long h_st[2];
     CUDA_CHECK(cudaMemcpyAsync(h_st, st_dev.p, sizeof(h_st), cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaMemcpyAsync(h_ctl.p, ctl.p, CTL_SIZE * sizeof(int), cudaMemcpyDeviceToHost, stream));

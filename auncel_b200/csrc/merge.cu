@@ -973,7 +973,14 @@ __global__ void finalize_kernel(RoundParams rp, TuneParams tp, float* D, long lo
             int p = (int)(code >> 32);
             unsigned off = (unsigned)(code & 0xffffffffu);
             int l = rp.ckeys[q * rp.nlist + p];
-            id = rp.ids[rp.list_off[l] + off];
+            if (rp.shard_rank >= 0) {
+                // the vector lives in exactly one shard; the others report -1 and an all-reduce(max) follows
+                const int sh = (int)(off >> SHARD_CODE_SHIFT);
+                off &= (1u << SHARD_CODE_SHIFT) - 1u;
+                id = sh == rp.shard_rank ? rp.ids[rp.list_off[l] + off] : -1;
+            } else {
+                id = rp.ids[rp.list_off[l] + off];
+            }
         }
         D[q * K + i] = dv;
         I[q * K + i] = id;

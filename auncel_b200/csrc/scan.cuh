@@ -45,6 +45,8 @@ struct QState {
 // slot_cnt[slot] = number of candidates | SLOT_SORTED when they are ordered by (distance, offset);
 // unordered slots (tensor-core rerank, short exact-scan results) are ordered by merge_check
 constexpr int SLOT_SORTED = 1 << 30;
+// sharded rounds (shard_rounds.cu): a candidate's 32-bit code is (shard << SHARD_CODE_SHIFT) | offset in the shard's list
+constexpr int SHARD_CODE_SHIFT = 26;
 
 struct RoundParams {
     // index
@@ -96,6 +98,7 @@ struct RoundParams {
     unsigned* cand_off;
     int* slot_cnt;
     QState st;
+    int shard_rank;       // >= 0: candidates carry their shard in the code; labels of other shards' vectors are -1 here
 };
 
 void launch_plan(const RoundParams& rp, cudaStream_t s);  // rp.filtered: only flagged pairs, slot counts kept

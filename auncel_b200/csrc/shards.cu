@@ -28,6 +28,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     ncclResult_t (*GetVersion)(int*) = nullptr;
 };
@@ -46,10 +47,11 @@ NcclApi& nccl() {
         api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
         api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
         api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+        api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
         api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
         api.GetVersion = (decltype(api.GetVersion))dlsym(h, "ncclGetVersion");
     });
-    AUNCEL_CHECK(api.handle && api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather,
+    AUNCEL_CHECK(api.handle && api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.AllReduce,
                  "NCCL (libnccl.so.2) could not be loaded; set AUNCEL_NCCL_LIB");
     return api;
 }
@@ -73,8 +75,30 @@ struct ShardGroup {
     // last call
     double local_ms = 0, allgather_ms = 0, merge_ms = 0;
     size_t allgather_bytes = 0;  // bytes this rank receives per call (world x packed table)
+    ShardExchange xchg;          // error-bounded rounds with single-index semantics (shard_rounds.cu)
+
+    // Route the local index's error-bounded and calibration searches through the round-wise candidate
+    // exchange: auncel_index_search_bounded* / auncel_index_calibrate on the local handle then are
+    // COLLECTIVE calls (every rank, same queries, same arguments) and return the single-index answer.
+    void set_bounded(bool on) {
+        if (!on || world == 1) {
+            if (ix->shard_x == &xchg) ix->shard_x = nullptr;
+            return;
+        }
+        xchg.rank = rank;
+        xchg.world = world;
+        ncclComm_t c = comm;
+        xchg.all_gather = [c](const void* send, void* recv, size_t bytes, cudaStream_t s) {
+            NCCL_CHECK(nccl().AllGather(send, recv, bytes, ncclInt8, c, s));
+        };
+        xchg.all_reduce_max = [c](long long* buf, size_t count, cudaStream_t s) {
+            NCCL_CHECK(nccl().AllReduce(buf, buf, count, ncclInt64, ncclMax, c, s));
+        };
+        ix->shard_x = &xchg;
+    }
 
     ~ShardGroup() {
+        if (ix && ix->shard_x == &xchg) ix->shard_x = nullptr;
         if (comm) nccl().CommDestroy(comm);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
@@ -217,6 +241,21 @@ int auncel_shard_group_search(AuncelShardGroup* g, int64_t n, const float* x, in
     CUDA_CHECK(cudaMemcpyAsync(labels, g->I.p, (size_t)n * k * sizeof(long long), cudaMemcpyDeviceToHost, ix.stream));
     CUDA_CHECK(cudaStreamSynchronize(ix.stream));
     SH_CATCH
+}
+
+int auncel_shard_group_set_bounded(AuncelShardGroup* g, int on) {
+    SH_TRY
+    AUNCEL_CHECK(g != nullptr, "null group");
+    g->g.set_bounded(on != 0);
+    SH_CATCH
+}
+
+int auncel_shard_group_get_exchange_stats(const AuncelShardGroup* g, double* out4) {
+    out4[0] = (double)g->g.xchg.exchanges;
+    out4[1] = (double)g->g.xchg.entries_sent;
+    out4[2] = (double)g->g.xchg.entries_recv;
+    out4[3] = (double)g->g.xchg.bytes_recv;
+    return 0;
 }
 
 int auncel_shard_group_get_stats(const AuncelShardGroup* g, double* out8) {

@@ -164,6 +164,23 @@ class NcclShardGroup:
                                             _p(D, _f), _p(I, _l)))
         return D, I
 
+    def set_bounded(self, on=True):
+        """Error-bounded search with SINGLE-INDEX semantics over the shards (csrc/shard_rounds.cu): while on,
+        Error_sys.search / sys_train / IndexIVFFlat.search_bounded on the local shard index are collective
+        calls -- every rank passes the same queries -- and answer as one index holding all vectors would
+        (IndexIVF.cpp:515-660): the ranks exchange each round's candidates before the stage replay."""
+        from ._lib import lib
+        from .index import _ck
+        _ck(lib().auncel_shard_group_set_bounded(self.h, 1 if on else 0))
+
+    def exchange_stats(self):
+        import ctypes as C
+
+        from ._lib import lib
+        out = (C.c_double * 4)()
+        lib().auncel_shard_group_get_exchange_stats(self.h, out)
+        return dict(zip(["exchanges", "entries_sent", "entries_all", "bytes_received"], [float(v) for v in out]))
+
     def stats(self):
         import ctypes as C
 

@@ -228,6 +228,22 @@ int auncel_shard_group_search_device(AuncelShardGroup* g, int64_t n, const float
  * [3] bytes received by the all-gather, [4] world, [5] rank, [6] NCCL version code */
 int auncel_shard_group_get_stats(const AuncelShardGroup* g, double* out8);
 
+/* Error-bounded search over the shards with SINGLE-INDEX semantics.
+ * The reference's own sharded mode (IndexShards.cpp:261-311) lets every shard stop on its own
+ * partial top-k.  With set_bounded(g, 1) the local shard handle's auncel_index_search_bounded*,
+ * auncel_index_calibrate and Error_sys-style calls become COLLECTIVE (all ranks, same queries and
+ * arguments, same pool budget) and reproduce IndexIVF.cpp:515-660 as run on ONE index holding all
+ * vectors: every rank scans its part of each probed list, the ranks exchange the per-(query, stage)
+ * candidates of a round (one ncclAllGather of a compact list), and every rank replays the
+ * stage-order merge + phi-U test on the union.  distances / my_nprobe / t_recalls are those of the
+ * single index bit for bit; labels differ only inside groups of equal distances.  max_codes and
+ * time_search are refused in this mode (they cut on list sizes, which are local).
+ * set_bounded(g, 0) restores per-shard behaviour.  get_exchange_stats (last search):
+ * out[0] exchanges (= rounds), [1] candidates this rank sent, [2] candidates all ranks sent,
+ * [3] bytes this rank received. */
+int auncel_shard_group_set_bounded(AuncelShardGroup* g, int on);
+int auncel_shard_group_get_exchange_stats(const AuncelShardGroup* g, double* out4);
+
 /* IndexIVF::copy_subset_to (IndexIVF.cpp:1055-1118): append to `other` (same centroids) the
  * entries selected by subset_type 1 (id % a1 == a2) or 2 (proportional in-list slice a1..a2
  * of ntotal).  This is how an index is split across GPUs (gpu/GpuAutoTune.cpp:201-220). */

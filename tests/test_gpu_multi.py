@@ -106,3 +106,100 @@ def test_shards_and_replicas_two_gpus():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert dict(out) == {0: "ok", 1: "ok"}
+
+
+def _bounded_worker(rank, world, port, out):
+    """Error-bounded search over shards with single-index semantics (csrc/shard_rounds.cu): calibration
+    traces, distances, my_nprobe and t_recalls of the sharded run equal the one-index run bit for bit."""
+    import torch.distributed as dist
+
+    import auncel_b200 as ab
+    from auncel_b200 import distributed as AD
+    from tests.util import assert_results_match, mixture
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        for metric, d, nlist, nb, K, qk, nq in [(ab.METRIC_L2, 32, 256, 60_000, 100, 10, 2600),
+                                                (ab.METRIC_INNER_PRODUCT, 96, 1024, 150_000, 100, 10, 3000),
+                                                (ab.METRIC_L2, 24, 128, 30_000, 16, 4, 400)]:
+            norm = metric == ab.METRIC_INNER_PRODUCT
+            xb = mixture(3, nb, d, norm)
+            xq = mixture(4, nq + 300, d, norm)
+            ids = np.arange(nb, dtype=np.int64) * 3 + 1
+            full = ab.IndexIVFFlat(d, nlist, metric, device=rank)
+            full.set_tune_mode()
+            full.train(xb[:: max(1, nb // (40 * nlist))], niter=3)
+            full.set_tune_off()
+            full.add_with_ids(xb, ids)
+            cent = full.centroids()
+            if norm:  # queries the reference serves in IP mode: first list holds >= K vectors
+                full.nprobe = 1
+                D1, I1 = full.search(xq, K)
+                xq = xq[(I1[:, K - 1] >= 0) & (D1[:, 0] <= 1.0)]
+            ts, ses = 200, min(nq, len(xq) - 200) // 10 * 10  # (Error_sys wants multiples of ten)
+            q = np.ascontiguousarray(xq[: ts + ses])
+            full.nprobe = nlist
+            gD, gI = full.search(q, K)
+            mine = AD.shard_mask(ids, world, rank)
+            shard = ab.IndexIVFFlat(d, nlist, metric, device=rank)
+            shard.set_centroids(cent)
+            shard.add_with_ids(xb[mine], ids[mine])
+            nsg = AD.NcclShardGroup(shard)
+            nsg.set_bounded(True)
+            res = []
+            for tc in (1, 2, 0):
+                row = []
+                for ix in (full, shard):
+                    ix.set_option("tensor_core_filter", tc)
+                    es = ab.Error_sys(ix, ts + ses, K)
+                    es.set_gt(gD, gI)
+                    es.sys_train(ts, q)
+                    es.set_topk(qk)
+                    es.setparam(3.0, 2.0)
+                    acc = np.full(ts + ses, 0.9, np.float32)
+                    acc[::3] = 0.97
+                    es.set_queries(ses, q, acc, ts + ses)
+                    es.profile = True
+                    D, I = es.search(ts)
+                    st = ix.stats()
+                    assert st["err_bits"] == 0, st
+                    row.append((ix.traces(), D, I, es.my_nprobe[ts:].copy(), es.t_recalls[ts:].copy(), st))
+                (tr_f, D_f, I_f, np_f, rc_f, st_f), (tr_s, D_s, I_s, np_s, rc_s, st_s) = row
+                assert len(tr_f) == len(tr_s) > 0
+                for a, b in zip(tr_f, tr_s):
+                    for x, y in zip(a, b):
+                        assert np.array_equal(x, y)
+                assert np.array_equal(np_f, np_s), (tc, int((np_f != np_s).sum()))
+                assert np.array_equal(D_f, D_s)
+                assert np.array_equal(rc_f, rc_s)
+                assert_results_match(D_s, I_s, D_f, I_f, what=f"sharded bounded tc={tc}")
+                assert (I_s == I_f).mean() > 0.999
+                xs = nsg.exchange_stats()
+                assert xs["exchanges"] == st_s["rounds"] > 0 and xs["entries_all"] >= xs["entries_sent"] > 0, xs
+                if tc == 2 and nq >= 2000:
+                    assert st_s["tc_rounds"] > 0
+                res.append(np_s)
+            assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2])
+            assert len(np.unique(res[0])) > 2  # the bound does vary the stop stage
+            # switching the exchange off restores the per-shard behaviour
+            nsg.set_bounded(False)
+            es = ab.Error_sys(shard, ts + ses, K)
+            es.set_gt(gD, gI)
+            es.sys_train(ts, q)
+            assert nsg.exchange_stats()["exchanges"] == xs["exchanges"]  # untouched: no exchange happened
+            del nsg
+        out[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bounded_shards_single_index_semantics_two_gpus():
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_bounded_worker, args=(2, port, out), nprocs=2, join=True)
+    assert dict(out) == {0: "ok", 1: "ok"}
