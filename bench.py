@@ -232,7 +232,9 @@ def shards_section(a, world, rank, local, steps, warmup):
     gp = torch.Generator(device=dev)
     gp.manual_seed(5)
     sel = torch.randperm(a.nb, generator=gp, device=dev)[:min(a.nb, 64 * a.nlist)]
+    sh.set_tune_mode()  # (the centroid-distance table interdis_cem: the error-bounded part below needs it)
     sh.train(base[sel].cpu().numpy(), niter=6)
+    sh.set_tune_off()
     cent = sh.centroids()
     ids = torch.arange(rank, a.nb, world, device=dev)
     sh.add_device(base[ids].contiguous(), ids.cpu().numpy())
@@ -275,12 +277,49 @@ def shards_section(a, world, rank, local, steps, warmup):
            "ms_per_step_wall": wall_ms, "local_search_ms": l_ms, "allgather_ms": a_ms, "merge_ms": m_ms,
            "allgather_bytes_per_step_per_rank": st["allgather_bytes"], "nccl_version": st["nccl_version"],
            "collective_share_of_step": (a_ms + m_ms) / step_ms, "setup_s": setup_s}
+    # ---- error-bounded search over the same shards, single-index semantics (csrc/shard_rounds.cu):
+    # the ranks exchange every round's candidates, so my_nprobe / distances are those of ONE index
+    bounded = None
+    if world > 1:
+        ncal = min(a.ncal, 1000)
+        qcal = W.make_vectors(shape, ncal, 987, dev)
+        sh.nprobe = a.nlist
+        gD = torch.empty(ncal, K, device=dev)
+        gI = torch.empty(ncal, K, device=dev, dtype=torch.int64)
+        g.search_device(qcal, K, gD, gI)                      # exhaustive over all shards: the ground truth
+        sh.nprobe = nprobe
+        g.set_bounded(True)
+        qcal_h, gD_h = qcal.cpu().numpy(), gD.cpu().numpy()
+        sh.calibrate(qcal_h, K, gD_h)                         # collective: the traces of the whole database
+        sh.set_params(*HYPER[a.eb])
+        acc_t = torch.full((a.nq,), 1.0 - a.eb, device=dev)
+        np_t = torch.zeros(a.nq, device=dev, dtype=torch.int64)
+        Db = torch.empty(a.nq, K, device=dev)
+        Ib = torch.empty(a.nq, K, device=dev, dtype=torch.int64)
+        bms = []
+        for it in range(2 + steps):
+            np_t.zero_()
+            sh.search_bounded_device(q, K, QUERY_TOPK, acc_t, np_t, Db, Ib)
+            if it >= 2:
+                bms.append(sh.stats()["search_ms"])
+        barrier()
+        tb = torch.tensor([float(np.mean(bms))], device=dev, dtype=torch.float64)
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        xs, stb = g.exchange_stats(), sh.stats()
+        bounded = {"workload": f"error bound {a.eb}, top-{QUERY_TOPK} of {K}, same shards and queries; single-index semantics",
+                   "parallelism": f"shards x{world}: per round 1 ncclAllGather of the candidates each rank's scan produced, "
+                                  "stage replay on every rank; 1 ncclAllReduce(max) of the labels",
+                   "value": a.nq / (float(tb[0]) / 1e3), "unit": "queries/s", "ms_per_step": float(tb[0]),
+                   "rounds": stb["rounds"], "tc_rounds": stb["tc_rounds"], "mean_my_nprobe": float(np_t.float().mean()),
+                   "candidates_sent_per_step_this_rank": xs["entries_sent"], "candidates_all_ranks": xs["entries_all"],
+                   "exchange_bytes_received_per_step_per_rank": xs["bytes_received"]}
+        g.set_bounded(False)
     # parity: the merged result equals the unsharded index (tests/test_merge.cpp:94-152 invariant)
     if world > 1:
         nchk = 512
         if rank == 0:
             one = ab.IndexIVFFlat(d, a.nlist, metric, device=local)
-            one.set_centroids(cent, compute_interdis=False)
+            one.set_centroids(cent)
             one.add_device(base)
             one.nprobe = nprobe
             D1 = torch.empty(nchk, K, device=dev)
@@ -289,8 +328,25 @@ def shards_section(a, world, rank, local, steps, warmup):
             out["parity_vs_single_index"] = {
                 "queries": nchk, "distances_bit_equal": bool(torch.equal(D1, D[:nchk])),
                 "labels_equal_frac": float((I1 == I[:nchk]).float().mean())}
+            one.calibrate(qcal_h, K, gD_h)
+            one.set_params(*HYPER[a.eb])
+            np1 = torch.zeros(nchk, device=dev, dtype=torch.int64)
+            one.search_bounded_device(q[:nchk], K, QUERY_TOPK, acc_t[:nchk].contiguous(), np1, D1, I1)
+            bounded["parity_vs_single_index"] = {
+                "queries": nchk, "my_nprobe_equal": bool(torch.equal(np1, np_t[:nchk])),
+                "distances_bit_equal": bool(torch.equal(D1, Db[:nchk])),
+                "labels_equal_frac": float((I1 == Ib[:nchk]).float().mean())}
+            # the same bounded batch on ONE GPU holding the whole database (what the shards are compared with)
+            one_ms = []
+            for it in range(2 + steps):
+                np_t.zero_()
+                one.search_bounded_device(q, K, QUERY_TOPK, acc_t, np_t, Db, Ib)
+                if it >= 2:
+                    one_ms.append(one.stats()["search_ms"])
+            bounded["single_gpu_ms_per_step"] = float(np.mean(one_ms))
             del one
         dist.barrier()
+        out["error_bounded"] = bounded
     del g, sh, base
     torch.cuda.empty_cache()
     return out
