@@ -589,9 +589,20 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
                     stop = true;
                     break;
                 }
-                const int c = min(raw & ~SLOT_SORTED, K);
-                if (T + c > KP) flush();
+                int c = min(raw & ~SLOT_SORTED, K);
                 const long slot = (long)a * rp.w + p;
+                if (rcnt == K && c > 4) {
+                    // only the prefix that beats the K-th value held at the last flush can still enter
+                    const float kth = sm.Rd[K - 1];
+                    int nb = 0;
+                    for (int i = lane; i < c; i += 32) {
+                        const float v = rp.cand_d[slot * rp.cap + i];
+                        nb += (metric == METRIC_L2 ? v < kth : v > kth) ? 1 : 0;
+                    }
+                    for (int o = 16; o > 0; o >>= 1) nb += __shfl_xor_sync(0xffffffffu, nb, o);
+                    c = nb;
+                }
+                if (T + c > KP) flush();
                 for (int i = lane; i < c; i += 32) {
                     uint32_t o = f2ord(rp.cand_d[slot * rp.cap + i]);
                     if (metric == METRIC_IP) o = ~o;
@@ -638,7 +649,21 @@ __global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams 
         for (int seg = 0; seg < nseg_s; seg++) {
             const long slot = redo ? (long)rp.redo_ord[pidx] * 4 + seg : pidx * nseg + seg;
             const int raw_cnt = (single && !redo) ? raw0 : slot_cnt[slot];
-            const int rc = min(raw_cnt & ~SLOT_SORTED, cap);  // entries present (unsorted wide slots: up to cap)
+            int rc = min(raw_cnt & ~SLOT_SORTED, cap);  // entries present (unsorted wide slots: up to cap)
+            if ((raw_cnt & SLOT_SORTED) && rcnt == K && rc > MC_INSERT_MAX) {
+                // The slot was filled against the threshold of the round's START; stages merged since then
+                // have tightened the K-th value.  Only candidates that beat it NOW can enter (the strict
+                // test of IndexIVFFlat.cpp:129), and in an ordered slot those are a prefix: usually a
+                // handful, which go through the insertion path instead of a 2 KP merge.
+                const float kth = sm.Rd[K - 1];
+                int nb = 0;
+                for (int i = lane; i < min(rc, K); i += 32) {
+                    const float v = cand_d[slot * cap + i];
+                    nb += (metric == METRIC_L2 ? v < kth : v > kth) ? 1 : 0;
+                }
+                for (int o = 16; o > 0; o >>= 1) nb += __shfl_xor_sync(0xffffffffu, nb, o);
+                rc = nb;
+            }
             const int c = min(rc, K);                          // entries that can matter
             if (c == 0) continue;
             const int rcnt_before = rcnt;
