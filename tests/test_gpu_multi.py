@@ -194,12 +194,17 @@ def _bounded_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_bounded_shards_single_index_semantics_two_gpus():
+@pytest.mark.parametrize("world", [2, 4])
+def test_bounded_shards_single_index_semantics(world):
+    """world 4: a pair's union can exceed 512 entries only from 6 shards on at K = 100; 4 shards still cover
+    the overflow pool with more than two contributors per pair."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_bounded_worker, args=(2, port, out), nprocs=2, join=True)
-    assert dict(out) == {0: "ok", 1: "ok"}
+    mp.spawn(_bounded_worker, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {r: "ok" for r in range(world)}
