@@ -27,7 +27,12 @@
 
 namespace auncel {
 
-constexpr int TC_THREADS = 352;   // TMA, MMA, 2 x 4 epilogue warps (one group per accumulator), tile scheduler
+#ifndef TC_EPI_GROUPS
+#define TC_EPI_GROUPS 3
+#endif
+constexpr int TC_EG = TC_EPI_GROUPS;            // epilogue groups of four warps (one warp per TMEM lane quarter)
+constexpr int TC_SCHED_WARP = 2 + 4 * TC_EG;     // warps: 0 TMA, 1 MMA, 2 .. 1 + 4 EG epilogue, then the tile scheduler
+constexpr int TC_THREADS = 32 * (TC_SCHED_WARP + 1);
 #ifndef TC_ASTAGES_CFG
 #define TC_ASTAGES_CFG 5
 #endif
@@ -157,9 +162,9 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
         mb_init(&b_empty, 1);
         for (int i = 0; i < 2; i++) {
             mb_init(&t_full[i], 1);
-            mb_init(&t_empty[i], 8);
+            mb_init(&t_empty[i], 4 * TC_EG);
             mb_init(&m_full[i], 1);
-            mb_init(&m_empty[i], 10);  // TMA warp + MMA warp + 8 epilogue warps
+            mb_init(&m_empty[i], 2 + 4 * TC_EG);  // TMA warp + MMA warp + the epilogue warps
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -172,7 +177,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
     tc_fence_after();
     const unsigned tmem_base = tmem_base_s;
 
-    if (warp == 10) {
+    if (warp == TC_SCHED_WARP) {
         // =========================== tile scheduler ===========================
         const int total_tiles = rp.ctl[CTL_TOTAL_TILES];
         for (unsigned t = 0;; t++) {
@@ -312,12 +317,13 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
             }
         }
         __syncwarp();
-    } else if (warp >= 2 && warp <= 9) {
+    } else if (warp >= 2 && warp < TC_SCHED_WARP) {
         // =========================== epilogue ===========================
-        // Two groups of four warps; both drain every accumulator, group g taking the 32-column
-        // chunks g, g+2, ...  The filter of a block must finish within the MMA time of the next
-        // one or the MMA warp stalls on t_empty; eight warps halve it and give every scheduler two
-        // epilogue warps to hide TMEM / shared-memory latencies.
+        // TC_EG groups of four warps; all drain every accumulator, group g taking the 32-column
+        // chunks g, g + TC_EG, ...  The filter of a block must finish within the MMA time of the next
+        // one or the MMA warp stalls on t_empty; twelve warps give every scheduler three epilogue
+        // warps to hide TMEM / shared-memory latencies (measured: 2 groups 2.07 ms for the 2-tile round,
+        // 3 groups 1.98, 4 groups 2.00; two query columns per 128-bit constant load: no gain).
         const int wq = warp & 3;  // TMEM lane quarter this warp may read
         const int grp = (warp - 2) >> 2;
         unsigned blkc = 0;
@@ -346,10 +352,27 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                 const float nvp = METRIC == METRIC_L2 ? nv * (1.f - ta.c2) : 0.f;
                 MB_WAIT(9, &t_full[buf], (blkc >> 1) & 1);
                 tc_fence_after();
-                for (int cg = grp; cg < ncg; cg += 2) {
+                for (int cg = grp; cg < ncg; cg += TC_EG) {
                     unsigned r[32];
                     tmem_ld32(tmem_base + ((unsigned)(wq * 32) << 16) + buf * 256 + cg * 32, r);
                     unsigned hits = 0;
+#ifdef TC_EPI_LDS128
+                    const float4* q4 = reinterpret_cast<const float4*>(mt->q) + cg * 16;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const float4 c = q4[j >> 1];  // the constants of two query columns per shared-memory load
+                        const float d0 = __uint_as_float(r[j]), d1 = __uint_as_float(r[j + 1]);
+                        bool p0, p1;
+                        if (METRIC == METRIC_L2) {
+                            p0 = __fmaf_rn(-c.x, snv, __fmaf_rn(-2.f, d0, nvp)) < c.y;
+                            p1 = __fmaf_rn(-c.z, snv, __fmaf_rn(-2.f, d1, nvp)) < c.w;
+                        } else {
+                            p0 = __fmaf_rn(c.x, snv, d0) > c.y;
+                            p1 = __fmaf_rn(c.z, snv, d1) > c.w;
+                        }
+                        hits |= ((p0 ? 1u : 0u) << j) | ((p1 ? 1u : 0u) << (j + 1));
+                    }
+#else
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const float2 c = mt->q[cg * 32 + j];
@@ -361,6 +384,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                             pass = __fmaf_rn(c.x, snv, dot) > c.y;
                         hits |= (pass ? 1u : 0u) << j;
                     }
+#endif
                     if (!valid || dead) hits = 0;
                     if (__any_sync(0xffffffffu, hits != 0)) {
                         // one atomic per warp and chunk: lane offsets by an inclusive scan of the hit counts
@@ -408,7 +432,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
             if ((unsigned)t2 < (unsigned)ta.cand_cap) ta.cand[t2] = ~0ull;
     }
 #ifdef TC_TIMING
-    if (blockIdx.x == 0 && lane == 0 && (warp <= 2 || warp == 6 || warp == 10)) {
+    if (blockIdx.x == 0 && lane == 0 && (warp <= 2 || warp == 6 || warp == TC_SCHED_WARP)) {
         const long long tot = clock64() - tc_t_begin;
         printf("tc_filter warp %d: total %lld | m_empty %lld m_full %lld/%lld/%lld b_empty %lld a_empty %lld b_full %lld t_empty %lld a_full %lld t_full %lld\n",
                warp, tot, tc_wait_acc[0], tc_wait_acc[1], tc_wait_acc[4], tc_wait_acc[8], tc_wait_acc[2], tc_wait_acc[3],
