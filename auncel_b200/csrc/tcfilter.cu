@@ -33,6 +33,9 @@ namespace auncel {
 constexpr int TC_EG = TC_EPI_GROUPS;            // epilogue groups of four warps (one warp per TMEM lane quarter)
 constexpr int TC_SCHED_WARP = 2 + 4 * TC_EG;     // warps: 0 TMA, 1 MMA, 2 .. 1 + 4 EG epilogue, then the tile scheduler
 constexpr int TC_THREADS = 32 * (TC_SCHED_WARP + 1);
+#ifndef TC_PREFETCH
+#define TC_PREFETCH 0  // experiment: row blocks requested into L2 ahead of the stage ring (measured: 0 is best, see below)
+#endif
 #ifndef TC_ASTAGES_CFG
 #define TC_ASTAGES_CFG 5
 #endif
@@ -93,6 +96,13 @@ __device__ __forceinline__ void tma2d(void* dst, const CUtensorMap* map, int c0,
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(s32(dst)),
                  "l"(map), "r"(c0), "r"(c1), "r"(s32(bar))
                  : "memory");
+}
+// L2 prefetch of one TMA box (no barrier, no shared memory).  Experiment (-DTC_PREFETCH=n): skipping every second
+// stage load does not shorten a filter round and no loads at all halve it, i.e. the ring of TC_ASTAGES x 16 KB is
+// latency-bound, so boxes were requested n row blocks ahead -- measured on the bench step (three filter rounds):
+// n = 0: 0.94 / 1.90 / 0.94 ms, 2: 0.94 / 1.98 / 0.98, 4: 1.00 / 2.01 / 1.00, 8: 1.28 / 2.10 / 1.26.  Off.
+__device__ __forceinline__ void tma2d_prefetch(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4,
 // LBO = 1 (unused for swizzled K-major), SBO = 1024 B between 8-row groups, version 1, layout 2.
@@ -262,10 +272,24 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                 MB_WAIT(2, &b_empty, (t & 1) ^ 1);
                 mb_expect_tx(&b_full, (unsigned)(nchunk * N * 128));
                 for (int c = 0; c < nchunk; c++) tma2d(Bsm + (size_t)c * N * 128, &bmap, c * 32, pair0, &b_full);
+#if TC_PREFETCH > 0
+                // row blocks [0, TC_PREFETCH) of the list go to L2 now, block blk + TC_PREFETCH when block blk is staged
+                for (int pb = 0; pb < min(nblk, TC_PREFETCH); pb++)
+                    for (int c = 0; c < nchunk; c++) tma2d_prefetch(&amap, c * 32, (int)(L0 + (long long)pb * 128));
+#endif
                 for (int blk = 0; blk < nblk; blk++)
                     for (int c = 0; c < nchunk; c++, ita++) {
+#if TC_PREFETCH > 0
+                        if (blk + TC_PREFETCH < nblk) tma2d_prefetch(&amap, c * 32, (int)(L0 + (long long)(blk + TC_PREFETCH) * 128));
+#endif
                         const int s = ita % TC_ASTAGES;
                         MB_WAIT(3, &a_empty[s], ((ita / TC_ASTAGES) & 1) ^ 1);
+#ifdef TC_EXP_SKIP_A  // experiment: only every TC_EXP_SKIP_A-th stage is really loaded (results are garbage)
+                        if (ita % TC_EXP_SKIP_A != 0) {
+                            mb_arrive(&a_full[s]);
+                            continue;
+                        }
+#endif
                         mb_expect_tx(&a_full[s], TC_A_BYTES);
                         tma2d(Asm + (size_t)s * TC_A_BYTES, &amap, c * 32, (int)(L0 + (long long)blk * 128), &a_full[s]);
                     }
@@ -386,6 +410,9 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                     }
 #endif
                     if (!valid || dead) hits = 0;
+#ifdef TC_EXP_NOAPPEND  // experiment: the filter pipeline without the survivor appends
+                    hits = 0;
+#endif
                     if (__any_sync(0xffffffffu, hits != 0)) {
                         // one atomic per warp and chunk: lane offsets by an inclusive scan of the hit counts
                         const int mine = __popc(hits);
