@@ -667,8 +667,19 @@ def cpu_baseline(a, S, np_gpu, D_gpu):
     nsample = cpu_sample_size(a, cores)
     R, O = build_reference(a, S)
     dt, D, mynp = cpu_sample_search(a, S, R, O, nsample, cores)
+    # the reference's latency mode: one query per call, one thread (eval/bound.cpp:390-396)
+    nlat = min(32, nsample)
+    R.clear_my_nprobe()
+    lat = []
+    for i in range(nlat):
+        t0 = time.perf_counter()
+        R.es_search(10 + i, 1, search_size=1, threads=1)
+        lat.append((time.perf_counter() - t0) * 1e3)
     R.close()
     return {"value": nsample / dt, "unit": "queries/s", "cores": cores, "kind": "reference",
+            "latency_mode": {"queries": nlat, "ms_per_query_mean": float(np.mean(lat)), "ms_per_query_p50": float(np.median(lat)),
+                             "note": "one Error_sys::search call per query on one thread (eval/bound.cpp:390-396); compare "
+                                     "hbm_bound.sift['1'].ms_per_call_wall"},
             "sample": f"first {nsample} test queries, one batched Error_sys::search on {cores} host threads drawing 4 "
                       f"queries at a time (unmodified reference, exact-difference coarse path, OpenBLAS unused), {dt:.2f} s",
             "setup": SETUP_NOTE,
