@@ -7,7 +7,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--eb", type=float, default=0.05)
 a0 = ap.parse_args()
 a = argparse.Namespace(shape="sift", nb=10_000_000, ncal=5000, nq=10000, nlist=4096, eb=0.1)
-S = B.build_everything(a, 0, 0)
+S = B.build_everything(a, 0, int(os.environ.get("QRANK", "0")))
 ix, dev = S["ix"], S["dev"]
 n = a.nq
 q = S["qtest"]

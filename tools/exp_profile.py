@@ -9,7 +9,7 @@ ap.add_argument("--nq", type=int, default=10000)
 ap.add_argument("--batch", type=int, default=0)
 a0 = ap.parse_args()
 a = argparse.Namespace(shape="sift", nb=10_000_000, ncal=5000, nq=a0.nq, nlist=4096, eb=0.1)
-S = B.build_everything(a, 0, 0)
+S = B.build_everything(a, 0, int(os.environ.get("QRANK", "0")))
 ix, dev = S["ix"], S["dev"]
 ix.set_params(*B.HYPER[0.1])
 n = a0.batch or a.nq
