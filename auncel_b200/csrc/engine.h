@@ -140,6 +140,7 @@ struct IvfIndex {
     DevBuf<long long> list_off;  // nlist + 1 (in vectors)
     std::vector<long long> h_list_off;
     alignas(64) unsigned char codes_tmap[128];  // CUtensorMap over `codes` (rebuilt by add)
+    alignas(64) unsigned char codes_tmap64[128];  // the same arena with 64-row boxes (tcfilter2.cu)
 
     // error model (device copies + host mirror)
     std::vector<float> h_arcos;
@@ -179,6 +180,7 @@ struct IvfIndex {
     DevBuf<int> redo_cnt, redo_ord;
     int tc_mode = 1;                         // 0 off, 1 automatic, 2 whenever every active heap is full
     int tc_audit = 0;                        // tests: redo every tensor-core round exactly and compare the slots
+    int tc_kernel = 0;                       // 0 automatic (TMEM-resident queries where d allows), 1 tcfilter.cu, 2 tcfilter2.cu
     DevBuf<unsigned char> audit_pool;
     DevBuf<int> audit_cnt;
     DevBuf<unsigned long long> audit_ctr;

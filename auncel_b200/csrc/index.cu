@@ -242,6 +242,7 @@ void IvfIndex::add_device(long n, const float* x_dev, const long long* ids_host,
     std::swap(ids.cap, nids.cap);
     h_list_off = new_off;
     make_codes_tensor_map(codes_tmap, codes.p, new_total, dpad);
+    make_codes_tensor_map(codes_tmap64, codes.p, new_total, dpad, 64);
     launch_row_norms(codes.p, new_total, dpad, vnorm.ensure(std::max<size_t>(new_total, 1)), stream);
     CUDA_CHECK(cudaStreamSynchronize(stream));
     ntotal += n;  // the reference counts skipped (-1) vectors too, IndexIVFFlat.cpp:79
@@ -569,7 +570,11 @@ void IvfIndex::search(const QueryBatch& qb) {
         bool use_tc = tc_mode == 2 ? (stats.rounds > 0 && min_rcnt >= K)
                                    : (tc_mode == 1 && mostly_full && r0 >= tc_min_r0 && avg_q >= 4.0 && (long)n_active * w >= 2048);
         if (use_tc && getenv("AUNCEL_NO_TC")) use_tc = false;
-        const int Ntc = tc_tile_queries(dpad);
+        // which filter kernel: queries resident in TMEM (all shared memory streams lists) where d allows
+        static const int tck_env = getenv("AUNCEL_TC_KERNEL") ? atoi(getenv("AUNCEL_TC_KERNEL")) : 0;
+        const int tck = tck_env ? tck_env : tc_kernel;
+        const bool tc_v2 = tck != 1 && tc2_tile_queries(dpad) > 0;
+        const int Ntc = tc_v2 ? tc2_tile_queries(dpad) : tc_tile_queries(dpad);
         if (use_tc) {
             S = 1;
             rp.qt = Ntc;
@@ -639,7 +644,7 @@ void IvfIndex::search(const QueryBatch& qb) {
             ta.cand = tc_cand.ensure(ta.cand_cap);
             ta.N = Ntc;
             alignas(64) unsigned char bmap[128];
-            make_queries_tensor_map_tc(bmap, rp.xq_sorted, (long long)n_active * w + 256, dpad, Ntc);
+            make_queries_tensor_map_tc(bmap, rp.xq_sorted, (long long)n_active * w + 256, dpad, tc_v2 ? 64 : Ntc);
             CUDA_CHECK(cudaMemsetAsync(ctl.p + CTL_NCAND, 0, 2 * sizeof(int), stream));  // NCAND, OVERFLOW
             rp.pair_flag = pair_flag.ensure((size_t)n_active * w);
             CUDA_CHECK(cudaMemsetAsync(rp.pair_flag, 0, (size_t)n_active * w * sizeof(int), stream));
@@ -652,7 +657,10 @@ void IvfIndex::search(const QueryBatch& qb) {
                 tc_ev.push_back(b);
             }
             CUDA_CHECK(cudaEventRecord(tc_ev[2 * tc_idx], stream));
-            launch_tc_filter(rp, ta, codes_tmap, bmap, num_sms, stream);
+            if (tc_v2)
+                launch_tc_filter2(rp, ta, codes_tmap64, bmap, num_sms, stream);
+            else
+                launch_tc_filter(rp, ta, codes_tmap, bmap, num_sms, stream);
             CUDA_CHECK(cudaEventRecord(tc_ev[2 * tc_idx + 1], stream));
             launch_rerank(rp, ta, num_sms, stream);
             CUDA_CHECK(cudaMemcpyAsync(h_ctl.p, ctl.p, CTL_SIZE * sizeof(int), cudaMemcpyDeviceToHost, stream));

@@ -658,8 +658,8 @@ static void make_tensor_map_2d(void* out_map, const float* base, long long nrows
     AUNCEL_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
 }
 
-void make_codes_tensor_map(void* out_map, const float* codes, long long nrows, int dpad) {
-    make_tensor_map_2d(out_map, codes, nrows, dpad, SCAN_VT, true);
+void make_codes_tensor_map(void* out_map, const float* codes, long long nrows, int dpad, int box_rows) {
+    make_tensor_map_2d(out_map, codes, nrows, dpad, box_rows, true);
 }
 
 void make_queries_tensor_map(void* out_map, const float* xq_sorted, long long nrows, int dpad) {

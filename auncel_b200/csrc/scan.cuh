@@ -105,6 +105,6 @@ void launch_plan(const RoundParams& rp, cudaStream_t s);  // rp.filtered: only f
 void launch_scan(const RoundParams& rp, const void* codes_map, const void* queries_map, int num_sms, cudaStream_t s);
 void make_queries_tensor_map(void* out_map, const float* xq_sorted, long long nrows, int dpad);
 // CUtensorMap (128 B, 64 B aligned) over the list arena [nrows x dpad] f32, box 128 rows x 32 floats
-void make_codes_tensor_map(void* out_map, const float* codes, long long nrows, int dpad);
+void make_codes_tensor_map(void* out_map, const float* codes, long long nrows, int dpad, int box_rows = 128);
 
 }  // namespace auncel

@@ -16,6 +16,11 @@ int tc_tile_queries(int dpad);
 void launch_row_norms(const float* x, long long n, int dpad, float* out, cudaStream_t s);
 void launch_tc_filter(const RoundParams& rp, const TcArgs& ta, const void* codes_map, const void* queries_map,
                       int num_sms, cudaStream_t s);
+// TMEM-resident queries (tcfilter2.cu): queries per tile for this dimension, 0 = not supported (d > 256);
+// both tensor maps with 64-row boxes
+int tc2_tile_queries(int dpad);
+void launch_tc_filter2(const RoundParams& rp, const TcArgs& ta, const void* codes_map64, const void* queries_map64,
+                       int num_sms, cudaStream_t s);
 void launch_rerank(const RoundParams& rp, const TcArgs& ta, int num_sms, cudaStream_t s);
 void launch_tc_audit(const RoundParams& tc, const float* ex_d, const unsigned* ex_off, const int* ex_cnt,
                      unsigned long long* ctr, cudaStream_t s);
