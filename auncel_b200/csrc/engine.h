@@ -180,7 +180,7 @@ struct IvfIndex {
     DevBuf<int> redo_cnt, redo_ord;
     int tc_mode = 1;                         // 0 off, 1 automatic, 2 whenever every active heap is full
     int tc_audit = 0;                        // tests: redo every tensor-core round exactly and compare the slots
-    int tc_kernel = 0;                       // 0 automatic (TMEM-resident queries where d allows), 1 tcfilter.cu, 2 tcfilter2.cu
+    int tc_kernel = 0;                       // 0 / 1 tcfilter.cu, 2 tcfilter2.cu (TMEM-resident queries; d <= 256)
     DevBuf<unsigned char> audit_pool;
     DevBuf<int> audit_cnt;
     DevBuf<unsigned long long> audit_ctr;

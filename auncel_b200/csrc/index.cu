@@ -570,10 +570,11 @@ void IvfIndex::search(const QueryBatch& qb) {
         bool use_tc = tc_mode == 2 ? (stats.rounds > 0 && min_rcnt >= K)
                                    : (tc_mode == 1 && mostly_full && r0 >= tc_min_r0 && avg_q >= 4.0 && (long)n_active * w >= 2048);
         if (use_tc && getenv("AUNCEL_NO_TC")) use_tc = false;
-        // which filter kernel: queries resident in TMEM (all shared memory streams lists) where d allows
+        // which filter kernel: tcfilter.cu (queries in shared memory), or on request tcfilter2.cu (queries
+        // resident in TMEM, all shared memory streams lists) -- measured slower, see its header
         static const int tck_env = getenv("AUNCEL_TC_KERNEL") ? atoi(getenv("AUNCEL_TC_KERNEL")) : 0;
         const int tck = tck_env ? tck_env : tc_kernel;
-        const bool tc_v2 = tck != 1 && tc2_tile_queries(dpad) > 0;
+        const bool tc_v2 = tck == 2 && tc2_tile_queries(dpad) > 0;
         const int Ntc = tc_v2 ? tc2_tile_queries(dpad) : tc_tile_queries(dpad);
         if (use_tc) {
             S = 1;

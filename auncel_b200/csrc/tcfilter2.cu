@@ -13,6 +13,14 @@
 // ring (TMA, ahead of the tile's first list block) and four loader warps move them from the stage into
 // TMEM with tcgen05.st once the previous tile's MMAs have retired.  Column budget (512): A at [0, G * KC),
 // KC = nchunk * 32 <= 256 / G; accumulators at [256, 512).  d > 256 stays with tcfilter.cu.
+// MEASURED (B200, bench step, three filter rounds): 1.95 / 3.13 / 1.57 ms against 0.97 / 1.96 / 0.97 ms of tcfilter.cu --
+// results bit-identical, but SLOWER, also with one query group and N = 128 (1.90 / 2.91 / 1.46).  The wait
+// attribution (-DTC2_TIMING) shows the MMA thread and the epilogue warps each busy ~60 % of the time and
+// waiting for each other the rest: an A operand in TMEM costs 128 lanes x 8 columns x 4 B = 4 KB of tensor-memory
+// reads per K = 8 instruction, on the read path the epilogue's tcgen05.ld (64 B per cycle) also uses; with only
+// d / 8 = 16 instructions per accumulator the operand reads are as large as the accumulator reads.  The layout
+// pays for GEMMs with a long K loop, not for this filter.  Kept as option "tc_kernel" = 2 (tests cover it);
+// the engine uses tcfilter.cu.
 // The bound, the survivor list and rerank_kernel are unchanged (tcfilter.cu); the epilogue is the
 // transpose of the old one: a thread owns a QUERY (TMEM lane) and walks over 32 list rows per tcgen05.ld.
 //
@@ -95,6 +103,14 @@ __device__ __forceinline__ void mb_wait_dbg(unsigned long long* b, unsigned pari
     }
 }
 #define MBW(site, b, par) mb_wait_dbg(b, par, site, t)
+#elif defined(TC2_TIMING)
+// wait-time attribution: cycles spent at each wait site, printed by CTA 0 at the end
+#define MBW(site, b, par)                      \
+    do {                                       \
+        long long t0_ = clock64();             \
+        mb_wait(b, par);                       \
+        t2_wait[site] += clock64() - t0_;      \
+    } while (0)
 #else
 #define MBW(site, b, par) mb_wait(b, par)
 #endif
@@ -128,6 +144,10 @@ tc_filter2_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap
     float2* rowc_all = reinterpret_cast<float2*>(ring + T2_RING + 2 * (T2_QMAX * 8 + 64));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef TC2_TIMING
+    long long t2_wait[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t2_begin = clock64();
+#endif
     const int dpad = rp.dpad;
     const int nchunk = (dpad + 31) / 32;
     const int KC = nchunk * 32;                 // TMEM columns of one query group
@@ -477,6 +497,16 @@ tc_filter2_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap
         for (int t2 = res_pos + lane; t2 < res_end; t2 += 32)  // unused tail of the last reservation: holes
             if ((unsigned)t2 < (unsigned)ta.cand_cap) ta.cand[t2] = ~0ull;
     }
+#ifdef TC2_TIMING
+    if (blockIdx.x == 0 && (warp <= 2 || warp == 6 || warp == T2_SCHED_WARP) && (lane == 0 || warp == 1)) {
+        bool me = lane == 0;
+        if (warp == 1) me = t2_wait[4] + t2_wait[11] + t2_wait[5] + t2_wait[6] > 0;  // the elected lane
+        if (me)
+            printf("tc_filter2 warp %d: total %lld | sched m_empty %lld | tma m_full %lld a_empty(q) %lld a_empty(list) %lld | mma m_full %lld q_full %lld t_empty %lld a_full %lld | load m_full %lld a_full %lld q_free %lld | epi m_full %lld t_full %lld\n",
+                   warp, clock64() - t2_begin, t2_wait[0], t2_wait[1], t2_wait[2], t2_wait[3], t2_wait[4], t2_wait[11], t2_wait[5],
+                   t2_wait[6], t2_wait[7], t2_wait[8], t2_wait[12], t2_wait[9], t2_wait[10]);
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
@@ -485,6 +515,8 @@ tc_filter2_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap
 // queries per tile of the TMEM-resident layout; 0 = this dimension needs tcfilter.cu
 int tc2_tile_queries(int dpad) {
     const int kc = (dpad + 31) / 32 * 32;
+    static const int g_env = getenv("AUNCEL_TC2_G") ? atoi(getenv("AUNCEL_TC2_G")) : 0;  // experiment: 1 = one query group per tile
+    if (g_env == 1) return kc <= 256 ? 128 : 0;
     return kc <= 128 ? 256 : kc <= 256 ? 128 : 0;
 }
 
