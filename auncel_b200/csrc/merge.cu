@@ -445,6 +445,11 @@ __device__ __forceinline__ unsigned cur_num_warp(const ErrModelView& m, const fl
 
 // --------------------------------------------------------------------------- merge + check
 constexpr int MC_WARPS = 4;
+#ifdef MC_MIN_BLOCKS
+#define MC_BOUNDS __launch_bounds__(MC_WARPS * 32, MC_MIN_BLOCKS)
+#else
+#define MC_BOUNDS __launch_bounds__(MC_WARPS * 32)
+#endif
 constexpr int MC_INSERT_MAX = 8;  // slots with at most this many candidates are merged by insertion
 
 template <int KP>
@@ -457,7 +462,7 @@ struct MergeSmem {
 };
 
 template <int KP>
-__global__ void __launch_bounds__(MC_WARPS * 32) merge_check_kernel(RoundParams rp, TuneParams tp) {
+__global__ void MC_BOUNDS merge_check_kernel(RoundParams rp, TuneParams tp) {
     __shared__ MergeSmem<KP> sm_all[MC_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     MergeSmem<KP>& sm = sm_all[warp];
