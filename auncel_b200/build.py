@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libauncel_b200.so")
-SOURCES = ["coarse.cu", "scan.cu", "tcfilter.cu", "tcfilter2.cu", "merge.cu", "merge_tables.cu", "kmeans.cu", "range.cu", "shards.cu", "shard_rounds.cu", "index.cu", "c_api.cu"]
+SOURCES = ["coarse.cu", "scan.cu", "tcfilter.cu", "tcfilter2.cu", "tcfilter3.cu", "merge.cu", "merge_tables.cu", "kmeans.cu", "range.cu", "shards.cu", "shard_rounds.cu", "index.cu", "c_api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-fmad=false",  # the reference build has no FMA; every product/sum rounds separately

@@ -174,13 +174,14 @@ struct IvfIndex {
     DevBuf<unsigned long long> pairs;
     DevBuf<float> q_sorted;
     DevBuf<float> vnorm, qnorm;              // squared norms of arena rows / of the batch's queries
+    DevBuf<float> list_nmax;                 // largest squared norm in every inverted list
     DevBuf<unsigned long long> tc_cand;      // survivors of the tensor-core filter
     DevBuf<int> pair_flag;                   // per slot: overflowed in a tensor-core round
     DevBuf<unsigned char> redo_pool;         // exact redo of those pairs: compact pool, 4 sub-slots per pair
     DevBuf<int> redo_cnt, redo_ord;
     int tc_mode = 1;                         // 0 off, 1 automatic, 2 whenever every active heap is full
     int tc_audit = 0;                        // tests: redo every tensor-core round exactly and compare the slots
-    int tc_kernel = 0;                       // 0 / 1 tcfilter.cu, 2 tcfilter2.cu (TMEM-resident queries; d <= 256)
+    int tc_kernel = 0;                       // 0 / 1 tcfilter.cu, 2 tcfilter2.cu (TMEM-resident queries; d <= 256), 3 tcfilter3.cu (CTA pairs)
     DevBuf<unsigned char> audit_pool;
     DevBuf<int> audit_cnt;
     DevBuf<unsigned long long> audit_ctr;

@@ -244,6 +244,7 @@ void IvfIndex::add_device(long n, const float* x_dev, const long long* ids_host,
     make_codes_tensor_map(codes_tmap, codes.p, new_total, dpad);
     make_codes_tensor_map(codes_tmap64, codes.p, new_total, dpad, 64);
     launch_row_norms(codes.p, new_total, dpad, vnorm.ensure(std::max<size_t>(new_total, 1)), stream);
+    launch_list_norm_max(vnorm.p, list_off.p, nlist, list_nmax.ensure(nlist), stream);
     CUDA_CHECK(cudaStreamSynchronize(stream));
     ntotal += n;  // the reference counts skipped (-1) vectors too, IndexIVFFlat.cpp:79
 }
@@ -575,7 +576,8 @@ void IvfIndex::search(const QueryBatch& qb) {
         static const int tck_env = getenv("AUNCEL_TC_KERNEL") ? atoi(getenv("AUNCEL_TC_KERNEL")) : 0;
         const int tck = tck_env ? tck_env : tc_kernel;
         const bool tc_v2 = tck == 2 && tc2_tile_queries(dpad) > 0;
-        const int Ntc = tc_v2 ? tc2_tile_queries(dpad) : tc_tile_queries(dpad);
+        const bool tc_v3 = tck == 3 && tc3_tile_queries(dpad) >= 32 && num_sms >= 2;  // CTA pairs (tcfilter3.cu)
+        const int Ntc = tc_v2 ? tc2_tile_queries(dpad) : tc_v3 ? tc3_tile_queries(dpad) : tc_tile_queries(dpad);
         if (use_tc) {
             S = 1;
             rp.qt = Ntc;
@@ -638,14 +640,16 @@ void IvfIndex::search(const QueryBatch& qb) {
             TcArgs ta;
             ta.vnorm = vnorm.p;
             ta.qnorm = qnorm.p;
+            ta.list_nmax = list_nmax.p;
             ta.c1 = 2.f * (1.02f / 512.f + (float)dpad / 2097152.f);
             ta.c2 = 1.f / 1048576.f;
             ta.c3 = 1.f / 16384.f;
             ta.cand_cap = (int)std::min<size_t>((size_t)64 << 20, std::max<size_t>((size_t)n_active * w * 32, 1 << 20));
             ta.cand = tc_cand.ensure(ta.cand_cap);
             ta.N = Ntc;
+            ta.dry = 0;
             alignas(64) unsigned char bmap[128];
-            make_queries_tensor_map_tc(bmap, rp.xq_sorted, (long long)n_active * w + 256, dpad, tc_v2 ? 64 : Ntc);
+            make_queries_tensor_map_tc(bmap, rp.xq_sorted, (long long)n_active * w + 256, dpad, tc_v2 ? 64 : tc_v3 ? Ntc / 2 : Ntc);
             CUDA_CHECK(cudaMemsetAsync(ctl.p + CTL_NCAND, 0, 2 * sizeof(int), stream));  // NCAND, OVERFLOW
             rp.pair_flag = pair_flag.ensure((size_t)n_active * w);
             CUDA_CHECK(cudaMemsetAsync(rp.pair_flag, 0, (size_t)n_active * w * sizeof(int), stream));
@@ -660,6 +664,18 @@ void IvfIndex::search(const QueryBatch& qb) {
             CUDA_CHECK(cudaEventRecord(tc_ev[2 * tc_idx], stream));
             if (tc_v2)
                 launch_tc_filter2(rp, ta, codes_tmap64, bmap, num_sms, stream);
+            else if (tc_v3) {
+                // experiment (AUNCEL_TC_DRY=1|2): the same launch first without its epilogue / without the appends,
+                // on the round's real inputs -- its duration shows in an ncu launch list
+                static const int dry_env = getenv("AUNCEL_TC_DRY") ? atoi(getenv("AUNCEL_TC_DRY")) : 0;
+                if (dry_env) {
+                    TcArgs td = ta;
+                    td.dry = dry_env;
+                    launch_tc_filter3(rp, td, codes_tmap, bmap, num_sms, stream);
+                    CUDA_CHECK(cudaMemsetAsync(ctl.p + CTL_TILE_COUNTER, 0, sizeof(int), stream));
+                }
+                launch_tc_filter3(rp, ta, codes_tmap, bmap, num_sms, stream);
+            }
             else
                 launch_tc_filter(rp, ta, codes_tmap, bmap, num_sms, stream);
             CUDA_CHECK(cudaEventRecord(tc_ev[2 * tc_idx + 1], stream));

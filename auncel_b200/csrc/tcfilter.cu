@@ -58,7 +58,7 @@ struct TileMeta {
     long long row0;  // first arena row of the list
     int L;           // list length
     int pad;
-    float2 q[TC_NMAX];  // (c1 * ||q||, rhs) per query column
+    float kq[TC_NMAX];  // per query column: the side of the filter test that does not depend on the row (see the scheduler)
 };
 
 #ifdef TC_TIMING
@@ -129,7 +129,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
             TileMeta* mt = &meta[m];
             int l = 0, cnt_l = 0, qt = 0, L = 0, Qt = 0, pair0 = 0, nblk = 0;
             long long L0 = 0;
-            float2 cq[TC_NMAX / 32];
+            float cq[TC_NMAX / 32];
             if (T < total_tiles) {  // decode and gather the constants BEFORE waiting for the meta slot
                 int lo = 0, hi = (int)rp.nlist;
                 while (hi - lo > 1) {
@@ -144,22 +144,28 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                 Qt = min(N, cnt_l - qt * N);
                 pair0 = rp.list_pair_off[l] + qt * N;
                 nblk = (L + 127) / 128;
+                // Filter test of a (row, query) pair, rows' part on the right:
+                //   L2:  ||v||^2 (1-c2) - 2 dot - c1 |q||v| < tau + c3|tau| - ||q||^2 (1-c2)
+                //        <=  dot + kq > 0.5 ||v||^2 (1-c2),   kq = 0.5 (rhs + c1 |q| max|v|) + slack
+                //   IP:  dot + c1/2 |q||v| > tau - c3|tau|   <=  dot > kq,   kq = tau - c3|tau| - c1/2 |q| max|v| - slack
+                // with max|v| over the LIST instead of the row's own norm (only the margin grows, nothing the exact
+                // test accepts is lost) and a slack for the roundings of this evaluation: one add and one compare
+                // per pair instead of two FMAs and a compare.
+                const float nmax = ta.list_nmax[l], snmax = sqrtf(nmax);
 #pragma unroll
                 for (int jj = 0; jj < TC_NMAX / 32; jj++) {
                     const int j = jj * 32 + lane;
-                    float2 c = make_float2(0.f, METRIC == METRIC_L2 ? -FLT_MAX : FLT_MAX);  // never passes
+                    float c = METRIC == METRIC_L2 ? -FLT_MAX : FLT_MAX;  // never passes
                     if (j < Qt) {
                         unsigned long long pr = rp.pairs[pair0 + j];
                         int q = rp.active[(int)(pr >> 32)];
                         float tau = rp.st.tau[q], nq = ta.qnorm[q];
                         if (METRIC == METRIC_L2) {
-                            // pass <=> nv(1-c2) - 2 dot - c1 |q||v|  <  tau + c3|tau| - nq(1-c2)
-                            c.x = ta.c1 * sqrtf(nq);
-                            c.y = tau + ta.c3 * fabsf(tau) - nq * (1.f - ta.c2);
+                            const float rhs = tau + ta.c3 * fabsf(tau) - nq * (1.f - ta.c2);
+                            c = 0.5f * (rhs + ta.c1 * sqrtf(nq) * snmax) + (nq + nmax) * (1.f / 1048576.f);
                         } else {
-                            // pass <=> dot + c1/2 |q||v|  >  tau - c3|tau|
-                            c.x = 0.5f * ta.c1 * sqrtf(nq);
-                            c.y = tau - ta.c3 * fabsf(tau);
+                            const float sq = sqrtf(nq) * snmax;  // >= |dot|
+                            c = tau - ta.c3 * fabsf(tau) - 0.5f * ta.c1 * sq - sq * (1.f / 1048576.f);
                         }
                     }
                     cq[jj] = c;
@@ -175,7 +181,7 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
             }
 #pragma unroll
             for (int jj = 0; jj < TC_NMAX / 32; jj++)
-                if (jj * 32 + lane < N) mt->q[jj * 32 + lane] = cq[jj];
+                if (jj * 32 + lane < N) mt->kq[jj * 32 + lane] = cq[jj];
             if (lane == 0) {
                 mt->flags = 0;
                 mt->nblk = nblk;
@@ -298,48 +304,44 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
             const bool dead = *reinterpret_cast<volatile int*>(&rp.ctl[CTL_OVERFLOW]) < 0;
             const int ncg = min(N, (mt->Qt + 31) / 32 * 32) / 32;
             const long long row0 = mt->row0;
+            float nv_next = (nblk > 0 && wq * 32 + lane < L) ? ta.vnorm[row0 + wq * 32 + lane] : 0.f;
             for (int blk = 0; blk < nblk; blk++, blkc++) {
                 const int buf = blkc & 1;
                 const int v = blk * 128 + wq * 32 + lane;
                 const bool valid = v < L;
-                const float nv = valid ? ta.vnorm[row0 + v] : 0.f;
-                const float snv = sqrtf(nv);
-                const float nvp = METRIC == METRIC_L2 ? nv * (1.f - ta.c2) : 0.f;
+                const float nv = nv_next;  // (fetched one block ahead: the load's latency stays off the t_full -> t_empty path)
+                {
+                    const int vn = v + 128;
+                    nv_next = (blk + 1 < nblk && vn < L) ? ta.vnorm[row0 + vn] : 0.f;
+                }
+                const float nvh = METRIC == METRIC_L2 ? 0.5f * (nv * (1.f - ta.c2)) : 0.f;  // the row's side of the test
                 MB_WAIT(9, &t_full[buf], (blkc >> 1) & 1);
                 tc_fence_after();
                 for (int cg = grp; cg < ncg; cg += TC_EG) {
                     unsigned r[32];
                     tmem_ld32(tmem_base + ((unsigned)(wq * 32) << 16) + buf * 256 + cg * 32, r);
                     unsigned hits = 0;
-#ifdef TC_EPI_LDS128
-                    const float4* q4 = reinterpret_cast<const float4*>(mt->q) + cg * 16;
+                    const float4* k4 = reinterpret_cast<const float4*>(mt->kq + cg * 32);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const float4 c = q4[j >> 1];  // the constants of two query columns per shared-memory load
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 k = k4[j >> 2];  // the constants of four query columns per shared-memory load
                         const float d0 = __uint_as_float(r[j]), d1 = __uint_as_float(r[j + 1]);
-                        bool p0, p1;
+                        const float d2 = __uint_as_float(r[j + 2]), d3 = __uint_as_float(r[j + 3]);
+                        bool p0, p1, p2, p3;
                         if (METRIC == METRIC_L2) {
-                            p0 = __fmaf_rn(-c.x, snv, __fmaf_rn(-2.f, d0, nvp)) < c.y;
-                            p1 = __fmaf_rn(-c.z, snv, __fmaf_rn(-2.f, d1, nvp)) < c.w;
+                            p0 = __fadd_rn(d0, k.x) > nvh;
+                            p1 = __fadd_rn(d1, k.y) > nvh;
+                            p2 = __fadd_rn(d2, k.z) > nvh;
+                            p3 = __fadd_rn(d3, k.w) > nvh;
                         } else {
-                            p0 = __fmaf_rn(c.x, snv, d0) > c.y;
-                            p1 = __fmaf_rn(c.z, snv, d1) > c.w;
+                            p0 = d0 > k.x;
+                            p1 = d1 > k.y;
+                            p2 = d2 > k.z;
+                            p3 = d3 > k.w;
                         }
-                        hits |= ((p0 ? 1u : 0u) << j) | ((p1 ? 1u : 0u) << (j + 1));
+                        hits |= ((p0 ? 1u : 0u) << j) | ((p1 ? 1u : 0u) << (j + 1)) | ((p2 ? 1u : 0u) << (j + 2)) |
+                                ((p3 ? 1u : 0u) << (j + 3));
                     }
-#else
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float2 c = mt->q[cg * 32 + j];
-                        const float dot = __uint_as_float(r[j]);
-                        bool pass;
-                        if (METRIC == METRIC_L2)
-                            pass = __fmaf_rn(-c.x, snv, __fmaf_rn(-2.f, dot, nvp)) < c.y;
-                        else
-                            pass = __fmaf_rn(c.x, snv, dot) > c.y;
-                        hits |= (pass ? 1u : 0u) << j;
-                    }
-#endif
                     if (!valid || dead) hits = 0;
 #ifdef TC_EXP_NOAPPEND  // experiment: the filter pipeline without the survivor appends
                     hits = 0;
@@ -516,6 +518,24 @@ __global__ void row_norms_kernel(const float* __restrict__ x, long long n, int d
 void launch_row_norms(const float* x, long long n, int dpad, float* out, cudaStream_t s) {
     if (n == 0) return;
     row_norms_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(x, n, dpad, out);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// max ||v||^2 of every inverted list (one warp per list)
+__global__ void list_norm_max_kernel(const float* __restrict__ vnorm, const long long* __restrict__ list_off, long nlist,
+                                     float* __restrict__ out) {
+    const long l = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (l >= nlist) return;
+    float m = 0.f;
+    for (long long i = list_off[l] + lane; i < list_off[l + 1]; i += 32) m = fmaxf(m, vnorm[i]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) out[l] = m;
+}
+
+void launch_list_norm_max(const float* vnorm, const long long* list_off, long nlist, float* out, cudaStream_t s) {
+    if (nlist == 0) return;
+    list_norm_max_kernel<<<(unsigned)((nlist * 32 + 255) / 256), 256, 0, s>>>(vnorm, list_off, nlist, out);
     CUDA_CHECK(cudaGetLastError());
 }
 

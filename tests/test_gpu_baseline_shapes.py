@@ -139,23 +139,25 @@ def test_tc_rounds_audited(pair):
         ix.set_option("tc_audit", 0)
 
 
-def test_tmem_resident_filter_kernel(pair):
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_alternative_filter_kernels(pair, kernel):
     """Option "tc_kernel" = 2 (tcfilter2.cu: queries resident in TMEM, TS-mode tcgen05.mma, the lists
-    streaming through a 208 KB ring whose length exceeds many tiles -- the lap-ahead case): audited
-    against the exact scan, and the search results equal those of the default kernel bit for bit."""
+    streaming through a 208 KB ring whose length exceeds many tiles -- the lap-ahead case) and = 3
+    (tcfilter3.cu: CTA pairs, tcgen05 cta_group::2, cross-CTA barriers): audited against the exact
+    scan, and the search results equal those of the default kernel bit for bit."""
     c, ix, R, xb, q = pair
-    if c["d"] > 256:
+    if kernel == 2 and c["d"] > 256:
         pytest.skip("tcfilter2.cu serves d <= 256")
     ix.nprobe = 64
     D1, I1 = ix.search(q[TS:], c["K"])
-    ix.set_option("tc_kernel", 2)
+    ix.set_option("tc_kernel", kernel)
     ix.set_option("tc_audit", 1)
     try:
         D2, I2 = ix.search(q[TS:], c["K"])
         st = ix.stats()
         assert st["tc_rounds"] > 0 and st["tc_audit_slots"] > 0 and st["tc_audit_bad"] == 0, st
         assert np.array_equal(D1, D2)
-        assert_results_match(D2, I2, D1, I1, what="tc_kernel 2 vs 1")
+        assert_results_match(D2, I2, D1, I1, what=f"tc_kernel {kernel} vs 1")
     finally:
         ix.set_option("tc_audit", 0)
         ix.set_option("tc_kernel", 0)

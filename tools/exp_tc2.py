@@ -18,7 +18,7 @@ D = torch.empty(n, 100, device=dev)
 I = torch.empty(n, 100, dtype=torch.int64, device=dev)
 ix.set_params(*B.HYPER[0.1])
 ref = None
-for kern in (1, 2, 1, 2):
+for kern in [int(k) for k in os.environ.get("KERNELS", "1,2,1,2").split(",")]:
     ix.set_option("tc_kernel", kern)
     ms = []
     for rep in range(6):

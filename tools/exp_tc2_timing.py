@@ -12,7 +12,7 @@ npb = torch.zeros(n, dtype=torch.int64, device=dev)
 D = torch.empty(n, 100, device=dev)
 I = torch.empty(n, 100, dtype=torch.int64, device=dev)
 ix.set_params(*B.HYPER[0.1])
-ix.set_option("tc_kernel", 2)
+ix.set_option("tc_kernel", int(os.environ.get("KERNEL", "2")))
 print("=== timed step", flush=True)
 ix.search_bounded_device(S["qtest"], 100, 10, acc, npb, D, I)
 torch.cuda.synchronize()
