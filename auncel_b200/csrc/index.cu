@@ -483,7 +483,7 @@ void IvfIndex::search(const QueryBatch& qb) {
 
     // ---- rounds
     int n_active = h_list_off[nlist] > 0 ? (int)n : 0;  // an empty index has nothing to scan
-    int min_rcnt = 0, not_full = (int)n;
+    int min_rcnt = 0, not_full = (int)n, rem_sum = 0;
     bool ties_done = false;
     const int tc_min_r0 = getenv("AUNCEL_TC_MIN_R0") ? atoi(getenv("AUNCEL_TC_MIN_R0")) : 1;
     const int wide_slot_r0 = getenv("AUNCEL_WIDE_R0") ? atoi(getenv("AUNCEL_WIDE_R0")) : 8;  // rounds starting below this rank get wide slots
@@ -577,7 +577,14 @@ void IvfIndex::search(const QueryBatch& qb) {
         const int tck = tck_env ? tck_env : tc_kernel;
         const bool tc_v2 = tck == 2 && tc2_tile_queries(dpad) > 0;
         const bool tc_v3 = tck == 3 && tc3_tile_queries(dpad) >= 32 && num_sms >= 2;  // CTA pairs (tcfilter3.cu)
-        const int Ntc = tc_v2 ? tc2_tile_queries(dpad) : tc_v3 ? tc3_tile_queries(dpad) : tc_tile_queries(dpad);
+        // d > 256: the resident query tile shrinks (32 queries at d = 960) and every list is re-streamed once per
+        // tile; when lists are probed by many queries the tile is streamed through the ring instead (256 queries
+        // per list pass, the tile re-read from L2 per 128-row block).  Pairs of this round: at most what the
+        // active queries have left up to their bounds (counted by compact_active).
+        const double est_pairs = std::min<double>((double)n_active * w, stats.rounds > 0 ? (double)rem_sum : 1e30);
+        const bool stream_b = !tc_v2 && !tc_v3 && tc_stream_queries(dpad) &&
+                              est_pairs / (double)std::min<long>(nlist, (long)n_active * w) >= 96.0;
+        const int Ntc = tc_v2 ? tc2_tile_queries(dpad) : tc_v3 ? tc3_tile_queries(dpad) : tc_tile_queries(dpad, stream_b);
         if (use_tc) {
             S = 1;
             rp.qt = Ntc;
@@ -648,6 +655,7 @@ void IvfIndex::search(const QueryBatch& qb) {
             ta.cand = tc_cand.ensure(ta.cand_cap);
             ta.N = Ntc;
             ta.dry = 0;
+            ta.stream_b = stream_b ? 1 : 0;
             alignas(64) unsigned char bmap[128];
             make_queries_tensor_map_tc(bmap, rp.xq_sorted, (long long)n_active * w + 256, dpad, tc_v2 ? 64 : tc_v3 ? Ntc / 2 : Ntc);
             CUDA_CHECK(cudaMemsetAsync(ctl.p + CTL_NCAND, 0, 2 * sizeof(int), stream));  // NCAND, OVERFLOW
@@ -769,6 +777,7 @@ void IvfIndex::search(const QueryBatch& qb) {
         n_active = h_ctl.p[CTL_N_ACTIVE];
         min_rcnt = h_ctl.p[CTL_MIN_RCNT];
         not_full = h_ctl.p[CTL_NOT_FULL];
+        rem_sum = h_ctl.p[CTL_REM_SUM];
         if (debug_rounds)
             round_log.push_back({r0, (int)w, rp.unsorted ? -1 : (int)(S * nsub), rp.n_active, h_ctl.p[CTL_TOTAL_TILES],
                                  h_ctl.p[CTL_TOTAL_PAIRS]});

@@ -968,6 +968,7 @@ __global__ void compact_active_kernel(RoundParams rp, int r1, int* active_out) {
         active_out[pos] = q;
         atomicMin(&rp.ctl[CTL_MIN_RCNT], rp.st.rcnt[q]);
         if (rp.st.rcnt[q] < rp.K) atomicAdd(&rp.ctl[CTL_NOT_FULL], 1);  // heaps still holding neutral slots
+        atomicAdd(&rp.ctl[CTL_REM_SUM], min(rp.st.bound[q] - r1, 4096));  // (the host sizes the next round's tiles with it)
     }
 }
 
@@ -976,6 +977,7 @@ void launch_compact_active(const RoundParams& rp, int r1, int* active_out, int* 
     CUDA_CHECK(cudaMemsetAsync(rp.ctl + CTL_N_ACTIVE, 0, sizeof(int), s));
     CUDA_CHECK(cudaMemsetAsync(rp.ctl + CTL_MIN_RCNT, 0x7f, sizeof(int), s));
     CUDA_CHECK(cudaMemsetAsync(rp.ctl + CTL_NOT_FULL, 0, sizeof(int), s));
+    CUDA_CHECK(cudaMemsetAsync(rp.ctl + CTL_REM_SUM, 0, sizeof(int), s));
     if (rp.n_active > 0) {
         compact_active_kernel<<<(unsigned)((rp.n_active + 255) / 256), 256, 0, s>>>(rp, r1, active_out);
         CUDA_CHECK(cudaGetLastError());

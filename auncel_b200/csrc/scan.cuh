@@ -7,7 +7,9 @@ namespace auncel {
 // control block slots (device ints, mirrored to pinned host memory once per round)
 enum { CTL_N_ACTIVE = 0, CTL_TOTAL_TILES = 1, CTL_TILE_COUNTER = 2, CTL_TOTAL_PAIRS = 3,
        CTL_ERR = 4, CTL_NFIX = 5, CTL_NCAND = 6, CTL_OVERFLOW = 7, CTL_MIN_RCNT = 8, CTL_NOT_FULL = 9, CTL_MERGE_NEXT = 10,
-       CTL_REDO_N = 11, CTL_SIZE = 16 };
+       CTL_REDO_N = 11,
+       CTL_REM_SUM = 12,  // sum over the still-active queries of min(stages left up to their bound, 4096)
+       CTL_SIZE = 16 };
 
 // per-query running state, SoA, carved from IvfIndex::state
 struct QState {

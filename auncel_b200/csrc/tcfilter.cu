@@ -47,6 +47,9 @@ constexpr int TC_ASTAGES = TC_ASTAGES_CFG;
 constexpr int TC_A_BYTES = 128 * 128;        // 128 rows x 32 f32
 constexpr int TC_B_MAX = TC_BKB_CFG * 1024;  // resident query tile: nchunk x N x 128 B
 constexpr int TC_NMAX = 256;
+constexpr int TC_SB_STAGES = 4;                  // streamed query tiles: stage = 16 KB of list rows + 256 queries x 128 B
+constexpr int TC_SB_BYTES = TC_A_BYTES + TC_NMAX * 128;
+static_assert(TC_SB_STAGES * TC_SB_BYTES <= TC_B_MAX + TC_ASTAGES * TC_A_BYTES, "streamed stages must fit the same shared memory");
 constexpr int TC_RES = 256;  // survivor-list entries an epilogue warp reserves per global atomic
 constexpr size_t TC_SMEM = 1024 + TC_B_MAX + (size_t)TC_ASTAGES * TC_A_BYTES + 2 * (TC_NMAX * 8 + 64);
 
@@ -204,7 +207,19 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
             __syncwarp();
             if (lane == 0) mb_arrive(&m_empty[m]);
             if (flags) break;
-            if (lane == 0) {
+            if (lane == 0 && ta.stream_b) {
+                // d > 256: a k-chunk of the query tile (256 x 32 f32) rides in every stage next to the list rows'
+                // k-chunk; the tile is re-read (from L2) for every 128-row block, but a list pass serves 256 queries
+                // instead of the 32 that fit resident at d = 960
+                for (int blk = 0; blk < nblk; blk++)
+                    for (int c = 0; c < nchunk; c++, ita++) {
+                        const int s = ita % TC_SB_STAGES;
+                        MB_WAIT(3, &a_empty[s], ((ita / TC_SB_STAGES) & 1) ^ 1);
+                        mb_expect_tx(&a_full[s], (unsigned)(TC_A_BYTES + N * 128));
+                        tma2d(smem + (size_t)s * TC_SB_BYTES, &amap, c * 32, (int)(L0 + (long long)blk * 128), &a_full[s]);
+                        tma2d(smem + (size_t)s * TC_SB_BYTES + TC_A_BYTES, &bmap, c * 32, pair0, &a_full[s]);
+                    }
+            } else if (lane == 0) {
                 // queries: resident for the whole tile, one swizzled [N x 32] block per k-chunk
                 MB_WAIT(2, &b_empty, (t & 1) ^ 1);
                 mb_expect_tx(&b_full, (unsigned)(nchunk * N * 128));
@@ -252,6 +267,30 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                 const unsigned idesc = idesc0 | ((unsigned)(Nt >> 3) << 17);
                 mb_arrive(&m_empty[m]);
                 if (flags) break;
+                if (ta.stream_b) {
+                    const unsigned long long sdesc0 = umma_desc(s32(smem));
+                    for (int blk = 0; blk < nblk; blk++, blkc++) {
+                        const int buf = blkc & 1;
+                        MB_WAIT(6, &t_empty[buf], ((blkc >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        const unsigned d_tmem = tmem_base + buf * 256;
+                        for (int c = 0; c < nchunk; c++) {
+                            MB_WAIT(7, &a_full[s], a_phase);
+                            tc_fence_after();
+                            const unsigned long long adesc = sdesc0 + s * (unsigned)(TC_SB_BYTES >> 4);
+                            const unsigned long long bdesc = adesc + (unsigned)(TC_A_BYTES >> 4);
+#pragma unroll
+                            for (int k = 0; k < 4; k++) umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (c | k) != 0);
+                            umma_commit(&a_empty[s]);
+                            if (++s == TC_SB_STAGES) {
+                                s = 0;
+                                a_phase ^= 1;
+                            }
+                        }
+                        umma_commit(&t_full[buf]);
+                    }
+                    continue;
+                }
                 MB_WAIT(5, &b_full, t & 1);
                 for (int blk = 0; blk < nblk; blk++, blkc++) {
                     const int buf = blkc & 1;
@@ -539,12 +578,19 @@ void launch_list_norm_max(const float* vnorm, const long long* list_off, long nl
     CUDA_CHECK(cudaGetLastError());
 }
 
-int tc_tile_queries(int dpad) {
+static int tc_resident_queries(int dpad) {
     int nchunk = (dpad + 31) / 32;
     int n = TC_B_MAX / (nchunk * 128);
-    n = std::min(n, TC_NMAX) / 32 * 32;  // the epilogue reads TMEM 32 columns at a time
-    return n;
+    return std::min(n, TC_NMAX) / 32 * 32;  // the epilogue reads TMEM 32 columns at a time
 }
+
+// fewer than 128 queries fit resident (d > 256): stream the query tile instead
+bool tc_stream_queries(int dpad) {
+    static const int off = getenv("AUNCEL_TC_NO_STREAM") ? 1 : 0;  // experiment: resident tiles at every dimension
+    return !off && tc_resident_queries(dpad) < 128;
+}
+
+int tc_tile_queries(int dpad, bool streamed) { return streamed ? TC_NMAX : tc_resident_queries(dpad); }
 
 void launch_tc_filter(const RoundParams& rp, const TcArgs& ta, const void* amap, const void* bmap, int num_sms,
                       cudaStream_t s) {

@@ -11,10 +11,13 @@ struct TcArgs {
     unsigned long long* cand;  // survivors: (pair position << 32) | offset in list
     int cand_cap;
     int N;                // queries per tile (multiple of 32, <= 256)
+    int stream_b;         // tcfilter.cu: 1 = the query tile is too large to stay resident (d > 256): its k-chunks
+                          // travel through the stage ring next to the list's, 256 queries per tile
     int dry;              // experiments (tcfilter3.cu): 1 = accumulators released unread, 2 = read and tested, nothing appended
 };
 
-int tc_tile_queries(int dpad);
+bool tc_stream_queries(int dpad);  // tcfilter.cu may stream the query tile for this dimension (tile = 256 queries)
+int tc_tile_queries(int dpad, bool streamed = false);
 void launch_row_norms(const float* x, long long n, int dpad, float* out, cudaStream_t s);
 void launch_list_norm_max(const float* vnorm, const long long* list_off, long nlist, float* out, cudaStream_t s);
 void launch_tc_filter(const RoundParams& rp, const TcArgs& ta, const void* codes_map, const void* queries_map,
