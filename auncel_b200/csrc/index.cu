@@ -395,7 +395,10 @@ void IvfIndex::search(const QueryBatch& qb) {
         xs = q_x.p;
     }
     // (a plain search reads only its nprobe best centroids: the partial ranking covers them)
-    coarse_rank(n, xs, qb.max_codes == 0 && !qb.time_tune && (qb.mode != 0 || nprobe + 1 < rank_rows_partial_width()));
+    // (Auncel mode: set_online and the first tie replay read ranks 0 .. max_num = nlist / 8 + 20, which a partial ranking
+    // covers up to nlist ~ 8000; beyond that every row is ranked completely)
+    coarse_rank(n, xs, qb.max_codes == 0 && !qb.time_tune &&
+                           (qb.mode != 0 ? max_num() + 1 < rank_rows_partial_width() : nprobe + 1 < rank_rows_partial_width()));
     if (tc_mode) launch_row_norms(xs, n, dpad, qnorm.ensure(n), stream);
     CUDA_CHECK(cudaEventRecord(ev2, stream));
     CUDA_CHECK(cudaMemsetAsync(ctl.p, 0, (CTL_SIZE + 8) * sizeof(int), stream));
