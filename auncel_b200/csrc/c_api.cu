@@ -608,6 +608,7 @@ int auncel_index_set_option(AuncelIndex* idx, const char* name, int value) {
     if (n == "tensor_core_filter") idx->ix.tc_mode = value;      // 0 off, 1 auto, 2 whenever heaps are full
     else if (n == "partial_rank") idx->ix.partial_rank_mode = value;  // 0 never, 1 large batches, 2 whenever nlist >= 4096
     else if (n == "tc_kernel") idx->ix.tc_kernel = value;        // 0 / 1 shared-memory queries, 2 TMEM-resident queries, 3 CTA pairs (measured alternatives)
+    else if (n == "tc_stream_min") idx->ix.tc_stream_min = value;  // d > 256: queries per list from which the query tile is streamed
     else if (n == "tc_audit") idx->ix.tc_audit = value;          // tests: exact rescan + comparison of every tensor-core round
     else if (n == "exact_ties") idx->ix.exact_ties = value != 0;  // replay the reference's heap order
     else AUNCEL_THROW(-2, "unknown option " + n);

@@ -181,6 +181,7 @@ struct IvfIndex {
     DevBuf<int> redo_cnt, redo_ord;
     int tc_mode = 1;                         // 0 off, 1 automatic, 2 whenever every active heap is full
     int tc_audit = 0;                        // tests: redo every tensor-core round exactly and compare the slots
+    int tc_stream_min = 96;                  // d > 256: stream the query tile when lists are probed by at least this many queries
     int tc_kernel = 0;                       // 0 / 1 tcfilter.cu, 2 tcfilter2.cu (TMEM-resident queries; d <= 256), 3 tcfilter3.cu (CTA pairs)
     DevBuf<unsigned char> audit_pool;
     DevBuf<int> audit_cnt;

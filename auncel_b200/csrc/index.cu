@@ -586,7 +586,7 @@ void IvfIndex::search(const QueryBatch& qb) {
         // active queries have left up to their bounds (counted by compact_active).
         const double est_pairs = std::min<double>((double)n_active * w, stats.rounds > 0 ? (double)rem_sum : 1e30);
         const bool stream_b = !tc_v2 && !tc_v3 && tc_stream_queries(dpad) &&
-                              est_pairs / (double)std::min<long>(nlist, (long)n_active * w) >= 96.0;
+                              est_pairs / (double)std::min<long>(nlist, (long)n_active * w) >= (double)tc_stream_min;
         const int Ntc = tc_v2 ? tc2_tile_queries(dpad) : tc_v3 ? tc3_tile_queries(dpad) : tc_tile_queries(dpad, stream_b);
         if (use_tc) {
             S = 1;

@@ -189,7 +189,9 @@ int auncel_index_get_round_stats(const AuncelIndex* idx, int max_rounds, double*
  * equal centroid distances; "partial_rank" 0 / 1 / 2: rank only the best 1024 centroids of a query up front and
  * complete a row when a round reads past them -- never / for batches >= 2048 (default) / always; "tc_audit" 0/1 (tests) redo every tensor-core round with the exact scan and
  * compare the candidate slots; "tc_kernel" 0 or 1 the default filter kernel (queries resident in shared memory), 2 queries
- * resident in tensor memory (d <= 256), 3 CTA pairs (tcgen05 cta_group::2) -- measured alternatives, docs/TC_FILTER_VARIANTS.md */
+ * resident in tensor memory (d <= 256), 3 CTA pairs (tcgen05 cta_group::2) -- measured alternatives, docs/TC_FILTER_VARIANTS.md;
+ * "tc_stream_min" (default 96): at d > 256 the filter streams the query tile through its stage ring when the lists of a
+ * round are probed by at least this many queries on average */
 int auncel_index_set_option(AuncelIndex* idx, const char* name, int value);
 
 /* scratch budget for per-round candidate pools, bytes (default 16 GiB) */

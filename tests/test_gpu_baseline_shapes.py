@@ -139,6 +139,28 @@ def test_tc_rounds_audited(pair):
         ix.set_option("tc_audit", 0)
 
 
+def test_streamed_query_tiles(pair):
+    """d > 256: the filter streams the query tile through its stage ring (256 queries per list pass) instead of
+    keeping 32 queries resident.  Forced on for every filter round (option tc_stream_min = 0), audited against
+    the exact scan, results equal to the resident-tile run bit for bit."""
+    c, ix, R, xb, q = pair
+    if c["d"] <= 256:
+        pytest.skip("query tiles stay resident at d <= 256")
+    ix.nprobe = 64
+    D1, I1 = ix.search(q[TS:], c["K"])
+    ix.set_option("tc_stream_min", 0)
+    ix.set_option("tc_audit", 1)
+    try:
+        D2, I2 = ix.search(q[TS:], c["K"])
+        st = ix.stats()
+        assert st["tc_rounds"] > 0 and st["tc_audit_slots"] > 0 and st["tc_audit_bad"] == 0, st
+        assert np.array_equal(D1, D2)
+        assert_results_match(D2, I2, D1, I1, what="streamed vs resident query tiles")
+    finally:
+        ix.set_option("tc_audit", 0)
+        ix.set_option("tc_stream_min", 96)
+
+
 @pytest.mark.parametrize("kernel", [2, 3])
 def test_alternative_filter_kernels(pair, kernel):
     """Option "tc_kernel" = 2 (tcfilter2.cu: queries resident in TMEM, TS-mode tcgen05.mma, the lists
