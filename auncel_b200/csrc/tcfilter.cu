@@ -163,7 +163,15 @@ tc_filter_kernel(RoundParams rp, TcArgs ta, const __grid_constant__ CUtensorMap 
                         unsigned long long pr = rp.pairs[pair0 + j];
                         int q = rp.active[(int)(pr >> 32)];
                         float tau = rp.st.tau[q], nq = ta.qnorm[q];
-                        if (METRIC == METRIC_L2) {
+                        if (tau == (METRIC == METRIC_L2 ? FLT_MAX : -FLT_MAX)) {
+                            // The query's heap is not full yet (its first lists held fewer than K vectors): no
+                            // threshold, every vector of the list would survive, overflow the slot and be redone
+                            // exactly anyway -- 73 such queries of the bench batch produced 5.5 M of the first filter
+                            // round's 5.6 M survivors.  Hand the pair to the exact redo right away: the column never
+                            // passes, the slot is flagged, the host sees a non-zero overflow count.
+                            rp.pair_flag[(long)(pr >> 32) * rp.w + (long)(pr & 0xffffffffu)] = 1;
+                            atomicAdd(&rp.ctl[CTL_OVERFLOW], 1);
+                        } else if (METRIC == METRIC_L2) {
                             const float rhs = tau + ta.c3 * fabsf(tau) - nq * (1.f - ta.c2);
                             c = 0.5f * (rhs + ta.c1 * sqrtf(nq) * snmax) + (nq + nmax) * (1.f / 1048576.f);
                         } else {
