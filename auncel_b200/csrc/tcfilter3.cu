@@ -9,10 +9,16 @@
 //   tensor cores read the other half from the peer's shared memory) and owns the accumulator rows of its A rows.
 // Half a query tile is 64 KB, so the ring grows from five to nine 16 KB stages per SM at the same bytes per MMA.
 // The bound, the survivor list, the epilogue and rerank_kernel are those of tcfilter.cu.
+// MEASURED (B200, bench step, three filter rounds): 1.04 / 2.05 / 1.00 ms against 0.94 / 1.83 / 0.90 ms of tcfilter.cu,
+// results bit-identical.  The ring no longer stalls the MMA thread (9 % waiting for a_full), and without the epilogue the
+// launches take 0.87 / 1.69 / 0.87 ms -- the 2-3-tile round is at the tensor pipe's real TF32 rate (~175 cycles per
+// N = 256 instruction), which no staging scheme improves; what the pair adds is cross-CTA latency on every accumulator
+// hand-over and half as many independent tile streams.  Kept as option "tc_kernel" = 3 (tests cover it); the engine uses
+// tcfilter.cu.  docs/TC_FILTER_VARIANTS.md has the comparison.
 //
 // Protocol (every barrier lives at the same shared-memory offset in both CTAs):
-//   a_full[s], b_full     leader's copy only: both producers' TMA loads complete_tx on it (address with the peer bit
-//                         cleared), the leader's producer arms it with the bytes of both
+//   a_full[s], b_full     leader's copy only: both producers' TMA loads complete_tx on it (its shared::cluster address,
+//                         `mapa`), the leader's producer arms it with the bytes of both
 //   a_empty[s], b_empty, t_full[i]   both copies, signalled by the leader's tcgen05.commit ... multicast::cluster
 //   t_empty[i]            leader's copy: its epilogue warps arrive on it, and the peer's forwarder thread once the peer's
 //                         epilogue warps have arrived on the peer's local t_done[i]
